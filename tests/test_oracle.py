@@ -1,0 +1,74 @@
+"""CPU tests: the oracle against the reference's stored outputs (tests/golden/) and
+the Philox restatement against Random123's known-answer vectors."""
+import numpy as np
+import pytest
+
+from oracle import gamil_oracle as G
+from oracle import philox as PX
+from tests.cases import Case, golden_names
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF), (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for ctr, key, want in kat:
+        got = PX.philox4x32([np.uint32(c) for c in ctr], key)
+        assert tuple(int(g) for g in got) == want
+
+
+def test_threshold_and_rates():
+    assert PX.drop_threshold(0.1) == 3277
+    assert PX.drop_threshold(0.0) == 0 and PX.drop_threshold(1.0) == 32768
+    k = PX.feature_keep(123, 0, 0, 4, 256, 0.1)
+    assert abs(k.mean() - (1 - 3277 / 32768)) < 2e-3
+    assert PX.feature_keep(1, 0, 0, 2, 8, 0.0).all()
+    assert not PX.feature_keep(1, 0, 0, 2, 8, 1.0).any()
+    # distinct (bag, t) give distinct streams; t-offset consistency (MC-sample sharding)
+    a = PX.feature_keep(5, 0, 0, 6, 16, 0.1)
+    b = PX.feature_keep(5, 0, 3, 3, 16, 0.1)
+    assert np.array_equal(a[3:], b)
+    assert not np.array_equal(a[0], a[1])
+    assert not np.array_equal(PX.feature_keep(5, 1, 0, 1, 16, 0.1), a[:1])
+    ka = PX.attn_keep(5, 0, 0, 6, 40, 3, 0.1)
+    assert np.array_equal(PX.attn_keep(5, 0, 2, 4, 40, 3, 0.1), ka[2:])
+
+
+def test_pack_bits_roundtrip():
+    rng = np.random.default_rng(0)
+    k = (rng.random((3, 5, 77)) < 0.9).astype(np.uint8)
+    w = PX.pack_bits(k)
+    assert w.shape == (3, 5, 3) and w.dtype == np.uint32
+    assert np.array_equal(PX.unpack_bits(w, 77), k)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_matches_reference(name):
+    """fp64 restatement vs the fp32 reference outputs stored by make_golden.py."""
+    c = Case(name)
+    out = G.mc_head_oracle(c.sd, c.H, c.keep_f, c.keep_a, c.p_f, c.p_a)
+    assert np.abs(out["Y"] - c.ref["Y"]).max() < 5e-6
+    assert np.abs(out["A"][::c.A_stride] - c.ref["A"]).max() < 2e-7
+    assert np.abs(out["prob_mean"] - c.ref["prob_mean"]).max() < 2e-6
+    assert np.abs(out["attn_mean"] - c.ref["attn_mean"]).max() < 1e-7
+    rel = np.abs(out["attn_m2"] - c.ref["attn_m2"]) / (np.abs(c.ref["attn_m2"]) + 1e-30)
+    assert rel.max() < 1e-3
+
+
+def test_welford_sumform_merge():
+    rng = np.random.default_rng(1)
+    x = rng.random((40, 7)) * 1e-3
+    parts = np.split(x, 8)
+    n = s1 = s2 = 0
+    for p in parts:
+        m = p.mean(0)
+        a, b, c = G.welford_sumform(len(p), m, ((p - m) ** 2).sum(0))
+        n, s1, s2 = n + a, s1 + b, s2 + c
+    cnt, mean, m2 = G.welford_from_sumform(n, s1, s2)
+    assert cnt == 40
+    assert np.allclose(mean, x.mean(0), rtol=1e-12)
+    assert np.allclose(m2, ((x - x.mean(0)) ** 2).sum(0), rtol=1e-9)
