@@ -1,0 +1,11 @@
+"""B200-native MC-dropout gated-attention MIL head (drop-in for the hot path of
+xkuubix/MonteCarlo-Gated-MIL, `MultiHeadGatedAttentionMIL.mc_inference`).
+
+Import as `mcmil_b200` (the repo-root alias package; this directory's name has a hyphen).
+"""
+from .head import HeadWeights, MCHeadResult, mc_head, export_masks  # noqa: F401
+from .model import MultiHeadGatedAttentionMIL, deactivate_batchnorm  # noqa: F401
+from . import distributed  # noqa: F401
+
+__all__ = ["HeadWeights", "MCHeadResult", "mc_head", "export_masks", "MultiHeadGatedAttentionMIL",
+           "deactivate_batchnorm", "distributed"]

@@ -1,0 +1,48 @@
+// common.cuh — shared constants and device-side tables of the MC-dropout GA-MIL head.
+// Math being implemented: /root/reference/model.py:280-316.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/mcmil_b200.h"
+
+namespace mcmil {
+
+constexpr int L = MCMIL_L;            // feature width            (model.py:139)
+constexpr int D = MCMIL_D;            // attention hidden width   (model.py:140)
+constexpr int MAXC = MCMIL_MAX_CLASSES;
+constexpr int TILE_ROWS = 128;        // patches per CTA-pair tile (64 per CTA)
+constexpr int HALF_ROWS = 64;
+constexpr int KSLICE = 64;            // fp16 elements per 128-byte swizzle row
+constexpr int NSLICE = L / KSLICE;    // 8 K-slices
+constexpr int SLICE_BYTES_A = HALF_ROWS * 128;   // 8 KB : 64 rows x 128 B
+constexpr int SLICE_BYTES_W = 128 * 128;         // 16 KB: 128 W-rows x 128 B
+constexpr int SLICE_BYTES_S = 8 * 128;           // 1 KB : 8 score rows x 128 B
+constexpr int TILE_H16_BYTES = 2 * NSLICE * SLICE_BYTES_A;  // 128 KB per pair tile
+
+// One pair tile = up to 128 consecutive patches of one bag.
+struct TileDesc {
+  int bag;      // local bag index
+  int n0;       // first patch (row within the bag)
+  int row0;     // first packed row (cu[bag] + n0)
+  int nrows;    // valid rows in this tile, 1..128
+  int gbag;     // global bag id keying the Philox masks (bag_ids[bag], or bag)
+  int pad_[3];
+};
+
+// Epilogue constants of one (V,U) parameter set, passed in the kernel-parameter constant bank.
+struct EpiConst {
+  float bv[D];          // attention_V bias
+  float hbu[D];         // 0.5 * attention_U bias       (sigmoid(x) = 0.5*tanh(0.5x)+0.5)
+  float hw[MAXC][D];    // 0.5 * attention_weights[c].weight
+  float bw[MAXC];       // attention_weights[c].bias
+};
+
+__host__ __device__ inline int drop_threshold(float p) {
+  if (p <= 0.f) return 0;
+  if (p >= 1.f) return 32768;
+  return (int)(p * 32768.0f + 0.5f);
+}
+__host__ __device__ inline float drop_scale(float p) { return p >= 1.f ? 0.f : 1.0f / (1.0f - p); }
+
+}  // namespace mcmil

@@ -1,0 +1,69 @@
+// internal.h — host-side objects behind the opaque C-ABI handles and the kernel launchers.
+#pragma once
+#include <vector>
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace mcmil {
+
+struct Weights {
+  int C = 0;            // num_classes
+  int shared = 1;
+  int S = 1;            // number of (V,U) parameter sets
+  // tcgen05 images, per set: [2 ranks][8 slices][16 KB] and [2 ranks][8 slices][1 KB]
+  uint8_t* d_wmain = nullptr;
+  uint8_t* d_wscore = nullptr;
+  // fp32 copies for the SIMT path: WT [S][512][256] (k-major; cols 0..127 V, 128..255 U)
+  float* d_wt = nullptr;
+  float* d_bv = nullptr;   // [S][128]
+  float* d_bu = nullptr;   // [S][128]
+  float* d_ww = nullptr;   // [C][128]
+  float* d_bw = nullptr;   // [C]
+  float* d_cls = nullptr;  // [C][512]
+  std::vector<EpiConst> epi;  // per set (host copy, passed by value to the kernel)
+};
+
+struct Plan {
+  int n_bags = 0, T = 0, C = 0;
+  int R = 0;        // total packed rows
+  int Rp = 0;       // R rounded up to 32 (row stride of the logit / score planes)
+  int n_tiles = 0;  // 128-row pair tiles
+  int max_n = 0;
+  std::vector<int32_t> cu;
+  std::vector<TileDesc> tiles;
+  int32_t* d_cu = nullptr;
+  TileDesc* d_tiles = nullptr;
+  int32_t* d_row2bag = nullptr;  // [R]
+  int32_t* d_gbag = nullptr;     // [n_bags] global bag ids
+  // workspace layout (byte offsets)
+  size_t off_h16 = 0, off_logit = 0, off_score = 0, off_rowstat = 0, ws_bytes = 0;
+};
+
+struct MaskSpec {
+  PhiloxKey key;
+  uint32_t thr_f, thr_a;
+  float sf, sa;          // 1/(1-p)
+  int t_offset, bag_offset;
+  const uint32_t* inj_feat;   // [T][R][16] or null
+  const uint32_t* inj_attn;   // [T][C][Rp/32] or null
+};
+
+// ---- launchers (each returns a cudaError_t and bumps *launches) ----
+cudaError_t launch_pack_weights(Weights& w, const float* attV_w, const float* attV_b, const float* attU_w,
+                                const float* attU_b, const float* attw_w, const float* attw_b,
+                                const float* cls_w, cudaStream_t st);
+cudaError_t launch_pack_h16(const Plan& p, const float* H, uint8_t* h16, cudaStream_t st, int* launches);
+cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const uint8_t* h16,
+                           float* logits, float* scores, float* dbg, cudaStream_t st, int* launches);
+cudaError_t launch_proj_simt(const Weights& w, const Plan& p, const MaskSpec& m, const float* H,
+                             float* logits, float* scores, cudaStream_t st, int* launches);
+cudaError_t launch_reduce(const Plan& p, const float* logits, const float* scores, float2* rowstat,
+                          float* Y, float* A, float* prob_mean, float* prob_m2, float* attn_mean,
+                          float* attn_m2, cudaStream_t st, int* launches);
+cudaError_t launch_export_masks(const Plan& p, const MaskSpec& m, uint32_t* feat_bits, uint32_t* attn_bits,
+                                cudaStream_t st);
+cudaError_t launch_welford_pack(const float* mean, const float* m2, double count, int n, double* packed,
+                                cudaStream_t st);
+cudaError_t launch_welford_unpack(const double* packed, int n, float* mean, float* m2, cudaStream_t st);
+
+}  // namespace mcmil

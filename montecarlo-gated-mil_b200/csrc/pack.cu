@@ -1,0 +1,189 @@
+// pack.cu — layout kernels: weights -> UMMA shared-memory images, features -> fp16 K-major
+// swizzled tiles, and the Philox keep-bit export used by the tests.
+//
+// Parameters packed here are the ones model.py:181-203 defines; the feature tile is the
+// H of model.py:276-277 (one bag's (N,512) ResNet features).
+#include "internal.h"
+
+namespace mcmil {
+
+// byte offset of element (row r, k in [0,64)) inside one 128-byte-swizzled K-major slice
+__host__ __device__ inline uint32_t sw128_off(int r, int k) {
+  return (uint32_t)r * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)k & 7u) * 2u;
+}
+
+// ------------------------------------------------------------------ weights
+// main image: [S][2 ranks][8 slices][128 rows][128 B]; rank r row j: j<64 -> V row d=64r+j, else U row d=64r+j-64
+__global__ void pack_wmain_kernel(const float* __restrict__ V, const float* __restrict__ U, int S,
+                                  __half* __restrict__ img) {
+  const int total = S * 2 * NSLICE * 128 * KSLICE;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kk = i % KSLICE;
+    const int j = (i / KSLICE) % 128;
+    const int q = (i / (KSLICE * 128)) % NSLICE;
+    const int r = (i / (KSLICE * 128 * NSLICE)) % 2;
+    const int s = i / (KSLICE * 128 * NSLICE * 2);
+    const int d = 64 * r + (j & 63);
+    const float* src = (j < 64 ? V : U) + ((size_t)s * D + d) * L + q * KSLICE + kk;
+    const size_t base = ((size_t)(s * 2 + r) * NSLICE + q) * SLICE_BYTES_W;
+    *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(img) + base + sw128_off(j, kk)) = __float2half_rn(*src);
+  }
+}
+
+// score image: [S][2 ranks][8 slices][8 rows][128 B]; rank 0 rows 0..3 = hi(fp16) of classifier rows,
+// rows 4..7 = lo = fp16(w - hi); rank 1 all zero.  shared: row i <-> head i; separate set s: row 0 <-> head s.
+__global__ void pack_wscore_kernel(const float* __restrict__ cls, int S, int C, int shared,
+                                   __half* __restrict__ img) {
+  const int total = S * 2 * NSLICE * 8 * KSLICE;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kk = i % KSLICE;
+    const int row = (i / KSLICE) % 8;
+    const int q = (i / (KSLICE * 8)) % NSLICE;
+    const int r = (i / (KSLICE * 8 * NSLICE)) % 2;
+    const int s = i / (KSLICE * 8 * NSLICE * 2);
+    float v = 0.f;
+    const int slot = row & 3;
+    const int head = shared ? slot : (slot == 0 ? s : -1);
+    if (r == 0 && head >= 0 && head < C) {
+      const float w = cls[(size_t)head * L + q * KSLICE + kk];
+      const float hi = __half2float(__float2half_rn(w));
+      v = (row < 4) ? hi : (w - hi);
+    }
+    const size_t base = ((size_t)(s * 2 + r) * NSLICE + q) * SLICE_BYTES_S;
+    *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(img) + base + sw128_off(row, kk)) = __float2half_rn(v);
+  }
+}
+
+// fp32 transposed copy for the SIMT path: WT[s][k][j], j<128 -> V[s][j][k], else U[s][j-128][k]
+__global__ void pack_wt_kernel(const float* __restrict__ V, const float* __restrict__ U, int S,
+                               float* __restrict__ WT) {
+  const int total = S * L * 256;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i % 256, k = (i / 256) % L, s = i / (256 * L);
+    WT[i] = (j < 128 ? V : U)[((size_t)s * D + (j & 127)) * L + k];
+  }
+}
+
+cudaError_t launch_pack_weights(Weights& w, const float* attV_w, const float* attV_b, const float* attU_w,
+                                const float* attU_b, const float* attw_w, const float* attw_b,
+                                const float* cls_w, cudaStream_t st) {
+  const int S = w.S, C = w.C;
+  pack_wmain_kernel<<<256, 256, 0, st>>>(attV_w, attU_w, S, reinterpret_cast<__half*>(w.d_wmain));
+  pack_wscore_kernel<<<64, 256, 0, st>>>(cls_w, S, C, w.shared, reinterpret_cast<__half*>(w.d_wscore));
+  pack_wt_kernel<<<256, 256, 0, st>>>(attV_w, attU_w, S, w.d_wt);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  cudaMemcpyAsync(w.d_bv, attV_b, sizeof(float) * S * D, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(w.d_bu, attU_b, sizeof(float) * S * D, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(w.d_ww, attw_w, sizeof(float) * C * D, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(w.d_bw, attw_b, sizeof(float) * C, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(w.d_cls, cls_w, sizeof(float) * C * L, cudaMemcpyDeviceToDevice, st);
+  // host copies of the epilogue constants (kernel-parameter constant bank)
+  std::vector<float> bv(S * D), bu(S * D), ww(C * D), bw(C);
+  cudaMemcpyAsync(bv.data(), attV_b, sizeof(float) * S * D, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(bu.data(), attU_b, sizeof(float) * S * D, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(ww.data(), attw_w, sizeof(float) * C * D, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(bw.data(), attw_b, sizeof(float) * C, cudaMemcpyDeviceToHost, st);
+  e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return e;
+  w.epi.assign(S, EpiConst{});
+  for (int s = 0; s < S; ++s) {
+    EpiConst& ec = w.epi[s];
+    for (int d = 0; d < D; ++d) {
+      ec.bv[d] = bv[s * D + d];
+      ec.hbu[d] = 0.5f * bu[s * D + d];
+    }
+    for (int c = 0; c < MAXC; ++c) {
+      // shared: slot c <-> head c; separate: slot 0 <-> head s
+      const int head = w.shared ? c : (c == 0 ? s : -1);
+      for (int d = 0; d < D; ++d) ec.hw[c][d] = (head >= 0 && head < C) ? 0.5f * ww[head * D + d] : 0.f;
+      ec.bw[c] = (head >= 0 && head < C) ? bw[head] : 0.f;
+    }
+  }
+  return cudaSuccess;
+}
+
+// ------------------------------------------------------------------ features -> fp16 tiles
+// h16: [n_tiles][2 ranks][8 slices][64 rows][128 B] swizzled; rows beyond the bag are zero.
+__global__ void pack_h16_kernel(const float* __restrict__ H, const TileDesc* __restrict__ tiles,
+                                uint8_t* __restrict__ h16) {
+  const int half = blockIdx.x;            // tile*2 + rank
+  const TileDesc td = tiles[half >> 1];
+  const int rank = half & 1;
+  uint8_t* dst = h16 + (size_t)half * (NSLICE * SLICE_BYTES_A);
+  for (int i = threadIdx.x; i < HALF_ROWS * (L / 8); i += blockDim.x) {
+    const int q = i & 63;                 // 8-feature chunk within the row
+    const int rr = i >> 6;                // row within the half tile
+    const int trow = rank * HALF_ROWS + rr;
+    uint4 packed = make_uint4(0, 0, 0, 0);
+    if (trow < td.nrows) {
+      const float4* src = reinterpret_cast<const float4*>(H + (size_t)(td.row0 + trow) * L + q * 8);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+      const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+      packed.x = *reinterpret_cast<const uint32_t*>(&h0);
+      packed.y = *reinterpret_cast<const uint32_t*>(&h1);
+      packed.z = *reinterpret_cast<const uint32_t*>(&h2);
+      packed.w = *reinterpret_cast<const uint32_t*>(&h3);
+    }
+    const int slice = q >> 3, c = q & 7;
+    *reinterpret_cast<uint4*>(dst + slice * SLICE_BYTES_A + rr * 128 + ((c ^ (rr & 7)) << 4)) = packed;
+  }
+}
+
+cudaError_t launch_pack_h16(const Plan& p, const float* H, uint8_t* h16, cudaStream_t st, int* launches) {
+  pack_h16_kernel<<<p.n_tiles * 2, 256, 0, st>>>(H, p.d_tiles, h16);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ mask export (tests)
+__global__ void export_feat_kernel(const int32_t* __restrict__ cu, const int32_t* __restrict__ row2bag,
+                                   const int32_t* __restrict__ gbag, int R, int T, MaskSpec m,
+                                   uint32_t* __restrict__ bits) {
+  // one thread per (t, row, word of 32 features)
+  const size_t total = (size_t)T * R * 16;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wd = (int)(i % 16);
+    const int g = (int)((i / 16) % R);
+    const int t = (int)(i / (16 * (size_t)R));
+    const int b = row2bag[g];
+    const uint32_t n = (uint32_t)(g - cu[b]);
+    uint32_t out = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      out |= feature_keep8((uint32_t)(wd * 4 + j), n, (uint32_t)(m.t_offset + t), (uint32_t)(m.bag_offset + gbag[b]),
+                           m.key, m.thr_f) << (8 * j);
+    bits[i] = out;
+  }
+}
+__global__ void export_attn_kernel(const int32_t* __restrict__ cu, const int32_t* __restrict__ row2bag,
+                                   const int32_t* __restrict__ gbag, int R, int Rp, int T, int C, MaskSpec m,
+                                   uint32_t* __restrict__ bits) {
+  const int Rw = Rp / 32;
+  const size_t total = (size_t)T * C * Rw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wd = (int)(i % Rw);
+    const int c = (int)((i / Rw) % C);
+    const int t = (int)(i / ((size_t)Rw * C));
+    uint32_t out = 0;
+    for (int j = 0; j < 32; ++j) {
+      const int g = wd * 32 + j;
+      if (g >= R) break;
+      const int b = row2bag[g];
+      const uint4 r = attn_words((uint32_t)(c >> 2), (uint32_t)(g - cu[b]), (uint32_t)(m.t_offset + t),
+                                 (uint32_t)(m.bag_offset + gbag[b]), m.key);
+      out |= (attn_keep_from(r, c, m.thr_a) ? 1u : 0u) << j;
+    }
+    bits[i] = out;
+  }
+}
+
+cudaError_t launch_export_masks(const Plan& p, const MaskSpec& m, uint32_t* feat_bits, uint32_t* attn_bits,
+                                cudaStream_t st) {
+  if (feat_bits) export_feat_kernel<<<1024, 256, 0, st>>>(p.d_cu, p.d_row2bag, p.d_gbag, p.R, p.T, m, feat_bits);
+  if (attn_bits) export_attn_kernel<<<256, 256, 0, st>>>(p.d_cu, p.d_row2bag, p.d_gbag, p.R, p.Rp, p.T, p.C, m, attn_bits);
+  return cudaGetLastError();
+}
+
+}  // namespace mcmil

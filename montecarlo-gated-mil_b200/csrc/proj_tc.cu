@@ -1,0 +1,382 @@
+// proj_tc.cu — the fused MC-dropout gated-attention projection on sm_100a tensor cores.
+//
+// Computes, for every MC sample t and patch n of a packed batch of bags (model.py:280-291,
+// and the classifier contraction of model.py:308-316 folded in as extra output columns):
+//     Hd[t,n,:]  = H[n,:] * keep_f[t,n,:]                      (1/(1-p_f) applied to the accumulators)
+//     logit[t,c,n] = ( sum_d tanh(Hd Wv^T + bv)_d * sigmoid(Hd Wu^T + bu)_d * w_c[d] + b_c ) * keep_a / (1-p_a)
+//     score[t,c,n] = Hd[t,n,:] . wc_c / (1-p_f)
+//
+// One persistent 2-CTA cluster per SM pair; the pair shares one tcgen05.mma.cta_group::2 of
+// M=128 (64 patches per CTA) x N=256 (V|U columns, half resident in each CTA's smem) x K=512.
+// Everything that is re-used across the T samples stays on chip:
+//   smem  : W (fp16, 128 KB/CTA, loaded once per kernel by TMA bulk copies), the fp16 feature
+//           tile (64 KB/CTA, one TMA load per work item), a 3-stage ring of masked A slices;
+//   TMEM  : two 128x256 fp32 accumulators (double buffered across t) + score columns.
+// Warp roles (14 warps): 0-3 epilogue (TMEM -> tanh/sigmoid/gate/w-dot -> logits),
+//   4-11 producers (Philox mask -> masked fp16 A slice, generic-proxy st.shared + proxy fence),
+//   12 MMA issuer (+TMEM alloc), 13 TMA loader.
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace mcmil {
+using namespace ptx;
+
+constexpr int TC_THREADS = 14 * 32;
+constexpr int NUM_STAGES = 3;
+constexpr int PRODUCER_WARP0 = 4, NUM_PRODUCER_WARPS = 8, MMA_WARP = 12, LOAD_WARP = 13;
+
+constexpr uint32_t SM_W = 0;
+constexpr uint32_t SM_WS = SM_W + NSLICE * SLICE_BYTES_W;          // 131072
+constexpr uint32_t SM_H = SM_WS + NSLICE * SLICE_BYTES_S;          // 139264
+constexpr uint32_t SM_RING = SM_H + NSLICE * SLICE_BYTES_A;        // 204800
+constexpr uint32_t SM_XCH = SM_RING + NUM_STAGES * SLICE_BYTES_A;  // 229376  [2][64][4] floats
+constexpr uint32_t SM_BAR = SM_XCH + 2 * HALF_ROWS * MAXC * 4;     // 231424
+constexpr uint32_t SM_TOTAL = SM_BAR + 256;                        // 231680 <= 232448 (227 KB)
+
+// barrier slots (8 bytes each) inside SM_BAR
+enum : uint32_t {
+  B_FULL = 0,                  // [3] leader only: masked A slice of both CTAs is in smem      (count 16)
+  B_EMPTY = B_FULL + 3,        // [3] per CTA: MMAs reading the stage have retired            (count 1)
+  B_TFULL = B_EMPTY + 3,       // [2] per CTA: accumulator buffer complete                    (count 1)
+  B_TEMPTY = B_TFULL + 2,      // [2] leader only: both CTAs' epilogues drained the buffer    (count 8)
+  B_WLOC = B_TEMPTY + 2,       // per CTA: W bulk copies landed                               (tx)
+  B_WREADY = B_WLOC + 1,       // leader only: both CTAs hold their W halves                  (count 2)
+  B_HFULL = B_WREADY + 1,      // per CTA: feature tile landed                                (tx)
+  B_HEMPTY = B_HFULL + 1,      // per CTA: producers finished with the feature tile           (count 8)
+  B_COUNT = B_HEMPTY + 1,
+  TMEM_SLOT = 30               // uint32 at SM_BAR + 8*30
+};
+
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TM_MAIN = 0;      // 2 buffers x 128 columns (2x2 layout of an M=128,N=256 pair MMA)
+constexpr uint32_t TM_SCORE = 256;   // 2 buffers x 32 columns (8 used)
+
+struct ProjParams {
+  const uint8_t* h16;      // [n_tiles][2][8][8 KB]
+  const uint8_t* wmain;    // this set: [2][8][16 KB]
+  const uint8_t* wscore;   // this set: [2][8][1 KB]
+  const TileDesc* tiles;
+  float* logits;           // [T][C][Rp]
+  float* scores;           // [T][C][Rp]
+  const uint32_t* inj_feat;  // [T][R][16] or null
+  const uint32_t* inj_attn;  // [T][C][Rp/32] or null
+  float* dbg;              // optional raw accumulator dump of each pair's first (tile, t)
+  int n_tiles, T, C, R, Rp;
+  int n_out;               // heads produced by this launch (shared: C, separate: 1)
+  int head0;               // first head index written by this launch
+  int t_offset, bag_offset;
+  uint32_t thr_f, thr_a;
+  float sf, hsf, sa;       // 1/(1-p_f), 0.5/(1-p_f), 1/(1-p_a)
+  PhiloxKey key;
+  EpiConst epi;
+};
+
+__device__ __forceinline__ uint32_t bar_addr(uint32_t sbase, uint32_t slot) { return sbase + SM_BAR + slot * 8; }
+
+// keep -> all-ones half lanes.  r holds two 16-bit uniform lanes; an element is kept iff
+// (lane & 0x7fff) >= thr.  Positive fp16 bit patterns order like their integer values and the
+// NaN patterns (> 0x7c00) must count as "large": compare |r| >=(unordered) thr as fp16x2.
+__device__ __forceinline__ uint32_t keep_mask2(uint32_t r, uint32_t thr2) {
+  uint32_t a, m;
+  asm("abs.f16x2 %0, %1;" : "=r"(a) : "r"(r));
+  asm("set.geu.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(thr2));
+  return m;
+}
+
+template <int HALF, int NOUT>
+__device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tcol, float (&acc)[MAXC],
+                                              float* dbg_row) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t v[16], u[16];
+    tmem_ld16(tcol + 16 * j, v);
+    tmem_ld16(tcol + 64 + 16 * j, u);
+    tmem_ld_wait();
+    if (dbg_row) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { dbg_row[16 * j + i] = __uint_as_float(v[i]); dbg_row[64 + 16 * j + i] = __uint_as_float(u[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int d = 64 * HALF + 16 * j + i;
+      const float av = tanh_approx(fmaf(__uint_as_float(v[i]), P.sf, P.epi.bv[d]));
+      const float au = tanh_approx(fmaf(__uint_as_float(u[i]), P.hsf, P.epi.hbu[d]));
+      const float g2 = fmaf(av, au, av);            // 2 * tanh(.) * sigmoid(.)
+#pragma unroll
+      for (int c = 0; c < NOUT; ++c) acc[c] = fmaf(g2, P.epi.hw[c][d], acc[c]);
+    }
+  }
+}
+
+template <int NOUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+proj_tc_kernel(const __grid_constant__ ProjParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  // contiguous slice of the (tile, t) unit space owned by this pair
+  const long long U = (long long)P.n_tiles * P.T;
+  const long long u_begin = U * pair / n_pairs, u_end = U * (pair + 1) / n_pairs;
+
+  if ((sbase & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(bar_addr(sbase, B_FULL + s), 2 * NUM_PRODUCER_WARPS); mbar_init(bar_addr(sbase, B_EMPTY + s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_addr(sbase, B_TFULL + b), 1); mbar_init(bar_addr(sbase, B_TEMPTY + b), 8); }
+    mbar_init(bar_addr(sbase, B_WLOC), 1);
+    mbar_init(bar_addr(sbase, B_WREADY), 2);
+    mbar_init(bar_addr(sbase, B_HFULL), 1);
+    mbar_init(bar_addr(sbase, B_HEMPTY), NUM_PRODUCER_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) {
+    tmem_alloc_cg2(sbase + SM_BAR + 8 * TMEM_SLOT, TMEM_COLS);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * TMEM_SLOT);
+
+  if (warp == LOAD_WARP) {
+    // ------------------------------------------------------------ TMA loader
+    if (lane == 0) {
+      const uint32_t wloc = bar_addr(sbase, B_WLOC);
+      mbar_expect_tx(wloc, NSLICE * (SLICE_BYTES_W + SLICE_BYTES_S));
+      for (int s = 0; s < NSLICE; ++s)
+        bulk_g2s(sbase + SM_W + s * SLICE_BYTES_W, P.wmain + (size_t)(rank * NSLICE + s) * SLICE_BYTES_W, SLICE_BYTES_W, wloc);
+      for (int s = 0; s < NSLICE; ++s)
+        bulk_g2s(sbase + SM_WS + s * SLICE_BYTES_S, P.wscore + (size_t)(rank * NSLICE + s) * SLICE_BYTES_S, SLICE_BYTES_S, wloc);
+      mbar_wait(wloc, 0);
+      mbar_arrive_cluster(mapa(bar_addr(sbase, B_WREADY), 0));
+      const uint32_t hfull = bar_addr(sbase, B_HFULL), hempty = bar_addr(sbase, B_HEMPTY);
+      int it = 0;
+      for (long long u = u_begin; u < u_end; ++it) {
+        const int ti = (int)(u / P.T);
+        const long long u_next = (long long)(ti + 1) * P.T;
+        if (it > 0) mbar_wait(hempty, (uint32_t)((it - 1) & 1));
+        mbar_expect_tx(hfull, NSLICE * SLICE_BYTES_A);
+        const uint8_t* src = P.h16 + ((size_t)ti * 2 + rank) * (NSLICE * SLICE_BYTES_A);
+        for (int s = 0; s < NSLICE; ++s)
+          bulk_g2s(sbase + SM_H + s * SLICE_BYTES_A, src + (size_t)s * SLICE_BYTES_A, SLICE_BYTES_A, hfull);
+        u = u_next < u_end ? u_next : u_end;
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t IDESC_MAIN = umma_idesc_f16(128, 256);
+      constexpr uint32_t IDESC_SCORE = umma_idesc_f16(128, 16);
+      mbar_wait(bar_addr(sbase, B_WREADY), 0);
+      tc_fence_after();
+      uint32_t k = 0, tc = 0;
+      for (long long u = u_begin; u < u_end; ++u, ++tc) {
+        const uint32_t buf = tc & 1;
+        mbar_wait(bar_addr(sbase, B_TEMPTY + buf), ((tc >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int s = 0; s < NSLICE; ++s, ++k) {
+          const uint32_t stage = k % NUM_STAGES, use = k / NUM_STAGES;
+          mbar_wait(bar_addr(sbase, B_FULL + stage), use & 1);
+          tc_fence_after();
+          const uint32_t a0 = sbase + SM_RING + stage * SLICE_BYTES_A;
+          const uint32_t b0 = sbase + SM_W + s * SLICE_BYTES_W;
+          const uint32_t s0 = sbase + SM_WS + s * SLICE_BYTES_S;
+#pragma unroll
+          for (int kk = 0; kk < KSLICE / 16; ++kk) {
+            const uint64_t ad = umma_desc_sw128(a0 + kk * 32);
+            umma_f16_cg2(tmem_base + TM_MAIN + buf * 128, ad, umma_desc_sw128(b0 + kk * 32), IDESC_MAIN, (s | kk) != 0);
+            umma_f16_cg2(tmem_base + TM_SCORE + buf * 32, ad, umma_desc_sw128(s0 + kk * 32), IDESC_SCORE, (s | kk) != 0);
+          }
+          umma_commit_cg2_mc(bar_addr(sbase, B_EMPTY + stage), 3);
+        }
+        umma_commit_cg2_mc(bar_addr(sbase, B_TFULL + buf), 3);
+      }
+    }
+  } else if (warp >= PRODUCER_WARP0) {
+    // ------------------------------------------------------------ producers: masked A slices
+    const int pw = warp - PRODUCER_WARP0;
+    const uint32_t full_leader = mapa(bar_addr(sbase, B_FULL), 0);
+    const uint32_t thr2 = P.thr_f | (P.thr_f << 16);
+    const int chunk = lane & 7;
+    int rowi[2]; uint32_t off[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      rowi[i] = pw * 8 + i * 4 + (lane >> 3);
+      off[i] = (uint32_t)rowi[i] * 128u + (uint32_t)((chunk ^ (rowi[i] & 7)) << 4);
+    }
+    uint32_t k = 0;
+    int it = 0;
+    for (long long u = u_begin; u < u_end; ++it) {
+      const int ti = (int)(u / P.T);
+      const int t_begin = (int)(u - (long long)ti * P.T);
+      const long long u_next = (long long)(ti + 1) * P.T;
+      const int t_end = (int)((u_next < u_end ? u_next : u_end) - (long long)ti * P.T);
+      const TileDesc td = P.tiles[ti];
+      mbar_wait(bar_addr(sbase, B_HFULL), (uint32_t)(it & 1));
+      const uint32_t bag = (uint32_t)(P.bag_offset + td.gbag);
+      for (int t = t_begin; t < t_end; ++t) {
+        const uint32_t tg = (uint32_t)(P.t_offset + t);
+        for (int s = 0; s < NSLICE; ++s, ++k) {
+          const uint32_t stage = k % NUM_STAGES, use = k / NUM_STAGES;
+          mbar_wait(bar_addr(sbase, B_EMPTY + stage), (use & 1) ^ 1);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint4 h = *reinterpret_cast<const uint4*>(smem + SM_H + s * SLICE_BYTES_A + off[i]);
+            uint4 o;
+            if (P.inj_feat == nullptr) {
+              const uint4 r = philox4x32((uint32_t)(s * 8 + chunk), (uint32_t)(td.n0 + (int)rank * HALF_ROWS + rowi[i]), tg, bag, P.key);
+              o.x = h.x & keep_mask2(r.x, thr2);
+              o.y = h.y & keep_mask2(r.y, thr2);
+              o.z = h.z & keep_mask2(r.z, thr2);
+              o.w = h.w & keep_mask2(r.w, thr2);
+            } else {
+              const int trow = (int)rank * HALF_ROWS + rowi[i];
+              uint32_t bits = 0;
+              if (trow < td.nrows)
+                bits = reinterpret_cast<const uint8_t*>(P.inj_feat)[((size_t)t * P.R + td.row0 + trow) * 64 + s * 8 + chunk];
+              o.x = h.x & ((bits & 1u ? 0x0000FFFFu : 0u) | (bits & 2u ? 0xFFFF0000u : 0u));
+              o.y = h.y & ((bits & 4u ? 0x0000FFFFu : 0u) | (bits & 8u ? 0xFFFF0000u : 0u));
+              o.z = h.z & ((bits & 16u ? 0x0000FFFFu : 0u) | (bits & 32u ? 0xFFFF0000u : 0u));
+              o.w = h.w & ((bits & 64u ? 0x0000FFFFu : 0u) | (bits & 128u ? 0xFFFF0000u : 0u));
+            }
+            *reinterpret_cast<uint4*>(smem + SM_RING + stage * SLICE_BYTES_A + off[i]) = o;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(full_leader + stage * 8);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_addr(sbase, B_HEMPTY));
+      u = u_next < u_end ? u_next : u_end;
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps 0..3
+    const int half = warp >> 1;                    // TMEM lanes 64..127 hold hidden units 64..127
+    const int r = (warp & 1) * 32 + lane;          // patch row within this CTA's 64-row half tile
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tempty_leader = mapa(bar_addr(sbase, B_TEMPTY), 0);
+    float* xch = reinterpret_cast<float*>(smem + SM_XCH);
+    uint32_t tc = 0;
+    for (long long u = u_begin; u < u_end;) {
+      const int ti = (int)(u / P.T);
+      const int t_begin = (int)(u - (long long)ti * P.T);
+      const long long u_next = (long long)(ti + 1) * P.T;
+      const int t_end = (int)((u_next < u_end ? u_next : u_end) - (long long)ti * P.T);
+      const TileDesc td = P.tiles[ti];
+      const int trow = (int)rank * HALF_ROWS + r;
+      const bool valid = trow < td.nrows;
+      const int g = td.row0 + trow;
+      for (int t = t_begin; t < t_end; ++t, ++tc) {
+        const uint32_t buf = tc & 1;
+        mbar_wait(bar_addr(sbase, B_TFULL + buf), (tc >> 1) & 1);
+        tc_fence_after();
+        float acc[MAXC] = {0.f, 0.f, 0.f, 0.f};
+        float* dbg_row = (P.dbg != nullptr && tc == 0)
+                             ? P.dbg + ((size_t)(pair * 2 + (int)rank) * 128 + warp * 32 + lane) * 136 : nullptr;
+        if (half == 0) epilogue_half<0, NOUT>(P, lane_base + TM_MAIN + buf * 128, acc, dbg_row);
+        else           epilogue_half<1, NOUT>(P, lane_base + TM_MAIN + buf * 128, acc, dbg_row);
+        uint32_t sc[8];
+        tmem_ld8(lane_base + TM_SCORE + buf * 32, sc);
+        tmem_ld_wait();
+        if (dbg_row) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dbg_row[128 + i] = __uint_as_float(sc[i]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader + buf * 8);
+        // combine the two hidden-unit halves of each patch row
+        float* x = xch + ((tc & 1) * HALF_ROWS + r) * MAXC;
+        if (half == 1) {
+#pragma unroll
+          for (int c = 0; c < NOUT; ++c) x[c] = acc[c];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (half == 0 && valid) {
+          const uint32_t tg = (uint32_t)(P.t_offset + t);
+          uint4 rnd = make_uint4(0, 0, 0, 0);
+          if (P.inj_attn == nullptr)
+            rnd = attn_words(0u, (uint32_t)(td.n0 + trow), tg, (uint32_t)(P.bag_offset + td.gbag), P.key);
+#pragma unroll
+          for (int c = 0; c < NOUT; ++c) {
+            {
+              const int head = P.head0 + c;
+              float logit = acc[c] + x[c] + P.epi.bw[c];
+              bool keep;
+              if (P.inj_attn == nullptr) keep = attn_keep_from(rnd, head, P.thr_a);
+              else keep = (P.inj_attn[((size_t)t * P.C + head) * (P.Rp >> 5) + (g >> 5)] >> (g & 31)) & 1u;
+              logit = keep ? logit * P.sa : 0.f;           // a dropped logit is 0, not -inf (model.py:291,305)
+              const size_t o = ((size_t)t * P.C + head) * P.Rp + g;
+              P.logits[o] = logit;
+              P.scores[o] = (__uint_as_float(sc[c]) + __uint_as_float(sc[4 + c])) * P.sf;
+            }
+          }
+        }
+      }
+      u = u_next < u_end ? u_next : u_end;
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+  }
+}
+
+cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const uint8_t* h16,
+                           float* logits, float* scores, float* dbg, cudaStream_t st, int* launches) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(proj_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(proj_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(proj_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(proj_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long units = (long long)p.n_tiles * p.T;
+  int n_pairs = sms / 2;
+  if (units < n_pairs) n_pairs = (int)units;
+  if (n_pairs < 1) return cudaSuccess;
+  for (int s = 0; s < w.S; ++s) {
+    ProjParams P;
+    P.h16 = h16;
+    P.wmain = w.d_wmain + (size_t)s * 2 * NSLICE * SLICE_BYTES_W;
+    P.wscore = w.d_wscore + (size_t)s * 2 * NSLICE * SLICE_BYTES_S;
+    P.tiles = p.d_tiles;
+    P.logits = logits; P.scores = scores;
+    P.inj_feat = m.inj_feat; P.inj_attn = m.inj_attn;
+    P.dbg = dbg;
+    P.n_tiles = p.n_tiles; P.T = p.T; P.C = p.C; P.R = p.R; P.Rp = p.Rp;
+    P.n_out = w.shared ? w.C : 1;
+    P.head0 = w.shared ? 0 : s;
+    P.t_offset = m.t_offset; P.bag_offset = m.bag_offset;
+    P.thr_f = m.thr_f; P.thr_a = m.thr_a;
+    P.sf = m.sf; P.hsf = 0.5f * m.sf; P.sa = m.sa;
+    P.key = m.key;
+    P.epi = w.epi[s];
+    switch (P.n_out) {
+      case 1: proj_tc_kernel<1><<<2 * n_pairs, TC_THREADS, SM_TOTAL, st>>>(P); break;
+      case 2: proj_tc_kernel<2><<<2 * n_pairs, TC_THREADS, SM_TOTAL, st>>>(P); break;
+      case 3: proj_tc_kernel<3><<<2 * n_pairs, TC_THREADS, SM_TOTAL, st>>>(P); break;
+      default: proj_tc_kernel<4><<<2 * n_pairs, TC_THREADS, SM_TOTAL, st>>>(P); break;
+    }
+    if (launches) ++*launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace mcmil

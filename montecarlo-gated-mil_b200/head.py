@@ -1,0 +1,273 @@
+"""Features-level entry points of the fused MC-dropout GA-MIL head.
+
+`mc_head` replaces the head part of `MultiHeadGatedAttentionMIL.mc_inference`
+(/root/reference/model.py:280-316) plus the MC statistics its callers take
+(/root/reference/infer.py:195,212-219; net_utils.py:207-208) by ONE call into the CUDA
+library (C-ABI in include/mcmil_b200.h).  torch is used for device memory and the stream only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+L_FEAT = 512
+D_HID = 128
+MAX_CLASSES = 4
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class HeadWeights:
+    """Device-side packed copy of the head parameters (reference state_dict keys,
+    /root/reference/model.py:181-203).  Re-create after the parameters change."""
+
+    def __init__(self, state_dict: dict, device="cuda"):
+        lib = _lib.load()
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("the MC-dropout head runs on CUDA only (no CPU fallback)")
+        sd = {k: v for k, v in state_dict.items() if not k.startswith("feature_extractor")}
+        C_ = 0
+        while f"classifiers.{C_}.weight" in sd:
+            C_ += 1
+        if not 1 <= C_ <= MAX_CLASSES:
+            raise NotImplementedError(f"num_classes must be in [1,{MAX_CLASSES}], got {C_}")
+        self.num_classes = C_
+        self.shared = "attention_V.0.weight" in sd
+        self.device = device
+
+        def dev(x):
+            return torch.as_tensor(x).detach().to(device=device, dtype=torch.float32).contiguous()
+
+        if self.shared:
+            Vw, Vb = dev(sd["attention_V.0.weight"])[None], dev(sd["attention_V.0.bias"])[None]
+            Uw, Ub = dev(sd["attention_U.0.weight"])[None], dev(sd["attention_U.0.bias"])[None]
+        else:
+            Vw = torch.stack([dev(sd[f"attention_V.{c}.0.weight"]) for c in range(C_)])
+            Vb = torch.stack([dev(sd[f"attention_V.{c}.0.bias"]) for c in range(C_)])
+            Uw = torch.stack([dev(sd[f"attention_U.{c}.0.weight"]) for c in range(C_)])
+            Ub = torch.stack([dev(sd[f"attention_U.{c}.0.bias"]) for c in range(C_)])
+        ww = torch.stack([dev(sd[f"attention_weights.{c}.weight"]).reshape(-1) for c in range(C_)])
+        bw = torch.stack([dev(sd[f"attention_weights.{c}.bias"]).reshape(()) for c in range(C_)])
+        cw = torch.stack([dev(sd[f"classifiers.{c}.weight"]).reshape(-1) for c in range(C_)])
+        S = 1 if self.shared else C_
+        if tuple(Vw.shape) != (S, D_HID, L_FEAT) or tuple(Uw.shape) != (S, D_HID, L_FEAT):
+            raise ValueError(f"attention_V/U weights must be ({D_HID},{L_FEAT}) (L=512, D=128), got {tuple(Vw.shape[1:])}")
+        if tuple(ww.shape) != (C_, D_HID) or tuple(cw.shape) != (C_, L_FEAT):
+            raise ValueError("attention_weights must be (1,128) and classifiers (1,512)")
+        tensors = [t.contiguous() for t in (Vw, Vb, Uw, Ub, ww, bw, cw)]
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.mcmil_weights_create(C.byref(handle), C_, int(self.shared), *[_ptr(t) for t in tensors],
+                                                _stream_ptr(device)), "mcmil_weights_create")
+        self._h = handle
+        self._lib = lib
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.mcmil_weights_destroy(h)
+            except Exception:
+                pass
+
+
+class _Plan:
+    def __init__(self, cu: np.ndarray, T: int, C_: int, device, bag_ids=None):
+        lib = _lib.load()
+        self.cu = np.ascontiguousarray(cu, dtype=np.int32)
+        ids = None
+        if bag_ids is not None:
+            self.bag_ids = np.ascontiguousarray(bag_ids, dtype=np.int32)
+            if self.bag_ids.shape != (len(self.cu) - 1,):
+                raise ValueError("bag_ids must have one entry per bag")
+            ids = self.bag_ids.ctypes.data_as(C.POINTER(C.c_int32))
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.mcmil_plan_create(C.byref(handle), self.cu.ctypes.data_as(C.POINTER(C.c_int32)), ids,
+                                             len(self.cu) - 1, int(T), int(C_), _stream_ptr(device)),
+                       "mcmil_plan_create")
+        self._h, self._lib = handle, lib
+        self.ws_bytes = int(lib.mcmil_plan_workspace_bytes(handle))
+        self.R = int(lib.mcmil_plan_total_rows(handle))
+        self.n_bags, self.T, self.C = len(self.cu) - 1, int(T), int(C_)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.mcmil_plan_destroy(h)
+            except Exception:
+                pass
+
+
+_plan_cache: dict = {}
+_workspaces: dict = {}
+
+
+def _get_plan(cu: np.ndarray, T: int, C_: int, device, bag_ids=None) -> _Plan:
+    ids_key = None if bag_ids is None else np.asarray(bag_ids, np.int32).tobytes()
+    key = (cu.tobytes(), ids_key, int(T), int(C_), str(device))
+    p = _plan_cache.get(key)
+    if p is None:
+        if len(_plan_cache) > 256:
+            _plan_cache.clear()
+        p = _plan_cache[key] = _Plan(cu, T, C_, device, bag_ids)
+    return p
+
+
+def _get_workspace(nbytes: int, device) -> torch.Tensor:
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20) + 1024, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    off = (-ws.data_ptr()) % 1024
+    return ws[off:off + nbytes]
+
+
+@dataclass
+class MCHeadResult:
+    """All tensors on the CUDA device, fp32.
+
+    Y          (n_bags, T, C)  per-sample logits            model.py:313-316
+    prob_mean  (n_bags, C)     mean_t softmax_c(Y)          net_utils.py:207-208
+    prob_m2    (n_bags, C)     sum_t (P - mean)^2
+    attn_mean  (C, R)          mean_t A[t,c,n]              infer.py:216,218 (patch level)
+    attn_m2    (C, R)          sum_t (A - mean)^2
+    A          (T, C, R) or None                            model.py:305
+    count      number of MC samples behind the statistics
+    cu_seqlens (n_bags+1,) numpy int32: bag b owns packed rows [cu[b], cu[b+1])
+    """
+    Y: torch.Tensor
+    prob_mean: torch.Tensor
+    prob_m2: torch.Tensor
+    attn_mean: torch.Tensor
+    attn_m2: torch.Tensor
+    A: Optional[torch.Tensor]
+    count: int
+    cu_seqlens: np.ndarray
+    launches: int = 0
+
+    def prob_var(self, ddof: int = 0):      # infer.py:52 uses np.std (ddof=0)
+        return self.prob_m2 / max(self.count - ddof, 1)
+
+    def attn_var(self, ddof: int = 1):      # infer.py:217,219 use torch.std (ddof=1)
+        return self.attn_m2 / max(self.count - ddof, 1)
+
+    def probs(self):
+        return torch.softmax(self.Y, dim=-1)   # infer.py:195 (tiny, caller-side)
+
+
+def mc_head(weights: HeadWeights, H: torch.Tensor, T: int, seed: int = 0,
+            p_f: float = 0.1, p_a: float = 0.1, cu_seqlens: Optional[Sequence[int]] = None,
+            keep_f_bits: Optional[torch.Tensor] = None, keep_a_bits: Optional[torch.Tensor] = None,
+            return_attention: bool = False, t_offset: int = 0, bag_offset: int = 0,
+            bag_ids: Optional[Sequence[int]] = None, impl: str = "tcgen05") -> MCHeadResult:
+    """Run T MC-dropout passes of the GA-MIL head on packed features.
+
+    H            (R, 512) fp32 CUDA, contiguous: one bag (cu_seqlens=None) or a packed batch
+    cu_seqlens   bag boundaries (host ints), len n_bags+1
+    bag_ids      global id of each bag (keys the Philox masks); default 0..n_bags-1 (+ bag_offset)
+    keep_f_bits  optional injected feature keep-mask, uint32/int32 (T, R, 16) CUDA
+    keep_a_bits  optional injected logit keep-mask, (T, C, ceil(R/32)) CUDA   (both or neither)
+    """
+    lib = _lib.load()
+    if not isinstance(H, torch.Tensor) or H.device.type != "cuda":
+        raise RuntimeError("mc_head: H must be a CUDA tensor (no CPU fallback)")
+    if H.dim() != 2 or H.shape[1] != L_FEAT:
+        raise ValueError(f"mc_head: H must be (R, {L_FEAT}), got {tuple(H.shape)}")
+    if H.dtype != torch.float32 or not H.is_contiguous():
+        raise ValueError("mc_head: H must be contiguous float32")
+    if H.device != weights.device:
+        raise ValueError("mc_head: H and the weights live on different devices")
+    if impl not in _lib.IMPLS:
+        raise ValueError(f"mc_head: impl must be one of {sorted(_lib.IMPLS)}")
+    R = H.shape[0]
+    cu = np.array([0, R], np.int32) if cu_seqlens is None else np.asarray(cu_seqlens, dtype=np.int64)
+    if cu.ndim != 1 or len(cu) < 2 or cu[0] != 0 or cu[-1] != R or np.any(np.diff(cu) <= 0):
+        raise ValueError("mc_head: cu_seqlens must start at 0, end at H.shape[0] and be strictly increasing")
+    cu = cu.astype(np.int32)
+    if T < 1:
+        raise ValueError("mc_head: T must be >= 1")
+    dev = H.device
+    C_ = weights.num_classes
+    plan = _get_plan(cu, T, C_, dev, bag_ids)
+    n_bags = plan.n_bags
+    if (keep_f_bits is None) != (keep_a_bits is None):
+        raise ValueError("mc_head: inject both masks or neither")
+    if keep_f_bits is not None:
+        Rw = (R + 31) // 32
+        if tuple(keep_f_bits.shape) != (T, R, 16) or tuple(keep_a_bits.shape) != (T, C_, Rw):
+            raise ValueError(f"mc_head: injected masks must be (T,R,16) and (T,C,{Rw}) words")
+        for m in (keep_f_bits, keep_a_bits):
+            if m.device != dev or m.element_size() != 4 or not m.is_contiguous():
+                raise ValueError("mc_head: injected masks must be contiguous 32-bit CUDA tensors")
+
+    with torch.cuda.device(dev):
+        Y = torch.empty((n_bags, T, C_), dtype=torch.float32, device=dev)
+        A = torch.empty((T, C_, R), dtype=torch.float32, device=dev) if return_attention else None
+        pm = torch.empty((n_bags, C_), dtype=torch.float32, device=dev)
+        pq = torch.empty((n_bags, C_), dtype=torch.float32, device=dev)
+        am = torch.empty((C_, R), dtype=torch.float32, device=dev)
+        aq = torch.empty((C_, R), dtype=torch.float32, device=dev)
+        ws = _get_workspace(plan.ws_bytes, dev)
+        code = lib.mcmil_head_forward(weights._h, plan._h, _ptr(H), int(t_offset), int(bag_offset),
+                                      int(seed) & 0xFFFFFFFFFFFFFFFF, float(p_f), float(p_a),
+                                      _ptr(keep_f_bits), _ptr(keep_a_bits), _lib.IMPLS[impl],
+                                      _ptr(Y), _ptr(A), _ptr(pm), _ptr(pq), _ptr(am), _ptr(aq),
+                                      _ptr(ws), ws.numel(), _stream_ptr(dev))
+        _lib.check(code, "mcmil_head_forward")
+        launches = int(lib.mcmil_last_launch_count())
+    return MCHeadResult(Y, pm, pq, am, aq, A, T, cu, launches)
+
+
+def export_masks(T: int, R_or_cu, num_classes: int, seed: int, p_f: float, p_a: float,
+                 t_offset: int = 0, bag_offset: int = 0, device="cuda"):
+    """The keep-bits the in-kernel Philox draws: (feat (T,R,16) int32, attn (T,C,ceil(R/32)) int32)."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    cu = np.array([0, int(R_or_cu)], np.int32) if np.isscalar(R_or_cu) else np.asarray(R_or_cu, np.int32)
+    plan = _get_plan(cu, T, num_classes, dev)
+    R = plan.R
+    with torch.cuda.device(dev):
+        fb = torch.zeros((T, R, 16), dtype=torch.int32, device=dev)
+        ab = torch.zeros((T, num_classes, (R + 31) // 32), dtype=torch.int32, device=dev)
+        _lib.check(lib.mcmil_export_masks(plan._h, int(t_offset), int(bag_offset), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                          float(p_f), float(p_a), _ptr(fb), _ptr(ab), _stream_ptr(dev)),
+                   "mcmil_export_masks")
+    return fb, ab
+
+
+def debug_proj_tc(weights: HeadWeights, H: torch.Tensor, T: int, seed: int, p_f: float, p_a: float,
+                  cu_seqlens=None, keep_f_bits=None, keep_a_bits=None, t_offset=0, bag_offset=0):
+    """Tests only: raw TMEM dump + logits/scores planes of the tcgen05 projection."""
+    lib = _lib.load()
+    dev = H.device
+    R = H.shape[0]
+    cu = np.array([0, R], np.int32) if cu_seqlens is None else np.asarray(cu_seqlens, np.int32)
+    plan = _get_plan(cu, T, weights.num_classes, dev)
+    Rp = (R + 31) // 32 * 32
+    with torch.cuda.device(dev):
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        dbg = torch.zeros((sms, 128, 136), dtype=torch.float32, device=dev)
+        lg = torch.zeros((T, weights.num_classes, Rp), dtype=torch.float32, device=dev)
+        sc = torch.zeros_like(lg)
+        ws = _get_workspace(plan.ws_bytes, dev)
+        _lib.check(lib.mcmil_debug_proj_tc(weights._h, plan._h, _ptr(H), int(t_offset), int(bag_offset),
+                                           int(seed), float(p_f), float(p_a), _ptr(keep_f_bits), _ptr(keep_a_bits),
+                                           _ptr(dbg), _ptr(lg), _ptr(sc), _ptr(ws), ws.numel(), _stream_ptr(dev)),
+                   "mcmil_debug_proj_tc")
+    return dbg, lg, sc

@@ -1,0 +1,144 @@
+"""Drop-in module: same constructor, parameter names / state_dict keys and `mc_inference`
+signature as the reference `MultiHeadGatedAttentionMIL` (/root/reference/model.py:134-328).
+
+Only the MC-dropout head is B200-native: the ResNet feature extractor runs once per bag in
+PyTorch (north_star; /root/reference/model.py:276-277) and its (N,512) output goes straight
+into the fused CUDA head.  `forward` (training / deterministic eval, /root/reference/
+model.py:211-253) is kept as plain torch so existing training scripts still run; it is not
+the accelerated path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .head import HeadWeights, MCHeadResult, mc_head
+
+
+class Identity(nn.Module):
+    def forward(self, x):
+        return x
+
+
+def _make_backbone(backbone: str, pretrained: bool):
+    import torchvision.models as tvm
+    ctor = {"r18": tvm.resnet18, "r34": tvm.resnet34, "r50": tvm.resnet50}
+    if not pretrained:
+        return tvm.resnet18()                       # the reference ignores `backbone` here (model.py:176-177)
+    weights = {"r18": tvm.ResNet18_Weights.IMAGENET1K_V1, "r34": tvm.ResNet34_Weights.IMAGENET1K_V1,
+               "r50": tvm.ResNet50_Weights.IMAGENET1K_V1}[backbone]
+    return ctor[backbone](weights=weights)
+
+
+class MultiHeadGatedAttentionMIL(nn.Module):
+    def __init__(self, num_classes=2, backbone="r18", pretrained=True, L=512, D=128,
+                 feature_dropout=0.1, attention_dropout=0.1, shared_attention=True, neptune_run=None):
+        super().__init__()
+        if L != 512 or D != 128:
+            raise NotImplementedError("the B200 head is built for L=512, D=128 (the reference defaults)")
+        self.fold_idx = None
+        self.neptune_run = neptune_run
+        self.L, self.D = L, D
+        self.num_classes = num_classes
+        self.shared_attention = shared_attention
+        self.feature_extractor = _make_backbone(backbone, pretrained)
+        self.feature_extractor.fc = Identity()
+        if shared_attention:
+            self.attention_V = nn.Sequential(nn.Linear(L, D), nn.Tanh())
+            self.attention_U = nn.Sequential(nn.Linear(L, D), nn.Sigmoid())
+        else:
+            self.attention_V = nn.ModuleList([nn.Sequential(nn.Linear(L, D), nn.Tanh()) for _ in range(num_classes)])
+            self.attention_U = nn.ModuleList([nn.Sequential(nn.Linear(L, D), nn.Sigmoid()) for _ in range(num_classes)])
+        self.attention_weights = nn.ModuleList([nn.Linear(D, 1) for _ in range(num_classes)])
+        self.classifiers = nn.ModuleList([nn.Linear(L, 1, bias=False) for _ in range(num_classes)])
+        self.feature_dropout = nn.Dropout(feature_dropout)
+        self.attention_dropouts = nn.ModuleList([nn.Dropout(attention_dropout) for _ in range(num_classes)])
+        self._packed = None          # (HeadWeights, version key)
+        self.mc_seed = 0             # Philox key of the next mc_inference call (auto-incremented)
+        self.last_result: MCHeadResult | None = None
+
+    # ------------------------------------------------------------------ plain-torch forward (not the hot path)
+    def forward(self, x, targets=None):
+        bs, n, ch, w, h = x.shape
+        H = self.feature_extractor(x.view(bs * n, ch, w, h))
+        H = self.feature_dropout(H).view(bs, n, -1)
+        M, A_all = [], []
+        for i in range(self.num_classes):
+            V = self.attention_V if self.shared_attention else self.attention_V[i]
+            U = self.attention_U if self.shared_attention else self.attention_U[i]
+            a = self.attention_weights[i](V(H) * U(H)).transpose(2, 1)
+            a = F.softmax(self.attention_dropouts[i](a), dim=2)
+            A_all.append(a)
+            M.append(torch.matmul(a, H))
+        M = torch.cat(M, dim=1)
+        A_all = torch.cat(A_all, dim=1)
+        Y = torch.cat([self.classifiers[i](M[:, i, :]) for i in range(self.num_classes)], dim=-1)
+        aux = None
+        if targets is not None:
+            d = F.pairwise_distance(A_all[:, 1, :], A_all[:, 0, :])
+            # model.py:405-426 (pairwise, margin 1.0, scale 0.5): push the heads apart on positives
+            aux = 0.5 * (torch.clamp(1.0 - d, min=0).mean() if targets.item() == 1 else d.mean())
+        return Y, A_all, aux
+
+    # ------------------------------------------------------------------ the B200 hot path
+    def _head_weights(self, device) -> HeadWeights:
+        params = [p for n, p in self.named_parameters() if not n.startswith("feature_extractor")]
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or self._packed[1] != key:
+            sd = {k: v for k, v in self.state_dict().items() if not k.startswith("feature_extractor")}
+            self._packed = (HeadWeights(sd, device), key)
+        return self._packed[0]
+
+    def extract_features(self, input_tensor):
+        """(1,N,3,H,W) -> (N,512): the extractor runs ONCE per bag (model.py:276-277)."""
+        bs, n = input_tensor.shape[:2]
+        if bs != 1:
+            raise RuntimeError("mc_inference supports bs == 1 only (as the reference, model.py:309)")
+        H = self.feature_extractor(input_tensor.view(-1, *input_tensor.shape[-3:]))
+        return H.view(n, -1).float().contiguous()
+
+    def mc_inference_stats(self, input_tensor, N=30, device="cuda", seed=None, return_attention=False,
+                           keep_f_bits=None, keep_a_bits=None, impl="tcgen05") -> MCHeadResult:
+        """Features once, then N fused MC-dropout passes; returns logits + Welford statistics."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("the fused MC-dropout head needs a CUDA device (there is no CPU fallback)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.eval()                                   # model.py:263
+        self.to(device)                               # model.py:264
+        for m in self.modules():                      # model.py:268-271: dropout stays in train mode
+            if isinstance(m, nn.Dropout):
+                m.train()
+        if seed is None:
+            seed, self.mc_seed = self.mc_seed, self.mc_seed + 1
+        with torch.no_grad():
+            H = self.extract_features(input_tensor.to(device))
+            res = mc_head(self._head_weights(device), H, int(N), seed=seed,
+                          p_f=float(self.feature_dropout.p), p_a=float(self.attention_dropouts[0].p),
+                          keep_f_bits=keep_f_bits, keep_a_bits=keep_a_bits,
+                          return_attention=return_attention, impl=impl)
+        self.last_result = res
+        return res
+
+    def mc_inference(self, input_tensor, N=30, device="cuda", targets=None, seed=None, legacy_tuple=False):
+        """Same contract as the reference (model.py:256-328): returns
+        (Y (N,1,C) logits, A (N,1,C,num_instances)); `legacy_tuple=True` appends the third
+        value (None) that the reference's committed callers unpack (infer.py:191,
+        net_utils.py:126,205).  `targets` is accepted and ignored: the reference computes
+        the auxiliary losses and then discards them (model.py:318-328).  The Welford
+        statistics of the same call are kept in `self.last_result`."""
+        res = self.mc_inference_stats(input_tensor, N=N, device=device, seed=seed, return_attention=True)
+        Y = res.Y.permute(1, 0, 2).contiguous()                     # (N, 1, C)
+        A = res.A.unsqueeze(1)                                      # (N, 1, C, n)
+        return (Y, A, None) if legacy_tuple else (Y, A)
+
+
+def deactivate_batchnorm(m):
+    """What every reference script applies before loading weights (main.py:16-20,
+    infer.py:105-109): BatchNorm uses per-bag batch statistics even in eval."""
+    if isinstance(m, nn.BatchNorm2d):
+        m.track_running_stats = False
+        m.running_mean = None
+        m.running_var = None

@@ -21,7 +21,7 @@ Mask convention (mirrored by `csrc/philox.cuh`):
       element e = l % 8 uses the 16-bit lane  (out[e >> 1] >> (16 * (e & 1))) & 0xffff
 * logit mask of (b, t, n), head c:
       ctr = (64 + c // 4, n, t, b);  lane = out[c % 4] & 0xffff
-* keep  <=>  (lane & 0x7fff) >= thr,   thr = round(p * 32768)   (15-bit Bernoulli,
+* keep  <=>  (lane & 0x7fff) >= thr,   thr = floor(p * 32768 + 0.5) in float32   (15-bit Bernoulli,
   p_eff = thr / 32768; p = 0.1 -> 3277 / 32768 = 0.100006)
 """
 from __future__ import annotations
@@ -59,7 +59,8 @@ def drop_threshold(p: float) -> int:
         return 0
     if p >= 1.0:
         return 32768
-    return int(round(p * 32768.0))
+    # same float32 arithmetic as csrc/common.cuh: (int)(p * 32768.0f + 0.5f)
+    return int(np.float32(p) * np.float32(32768.0) + np.float32(0.5))
 
 
 def _key(seed: int):

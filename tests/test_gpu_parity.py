@@ -1,0 +1,251 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every call goes through the C-ABI
+of montecarlo-gated-mil_b200/lib/libmcmil_b200.so (ctypes), never through the oracle.
+
+Tolerances are north_star's: probabilities within 1e-3 relative, attention mean / variance within
+1e-4 absolute (fp32 accumulation) — plus tighter relative bounds so regressions stay visible
+(attention values are O(1/N)).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gamil_oracle as G
+from oracle import philox as PX
+from tests.cases import Case, golden_names
+
+pytestmark = pytest.mark.gpu
+
+PROB_RTOL = 1e-3
+ATTN_ATOL = 1e-4
+# relative bounds per implementation: (attention mean, attention M2, logits abs)
+REL = {"simt_fp32": (2e-5, 2e-3, 2e-5), "tcgen05": (3e-3, 3e-2, 2e-3)}
+IMPLS = ["simt_fp32", "tcgen05"]
+
+
+@pytest.fixture(scope="module")
+def mm():
+    import mcmil_b200
+    assert torch.cuda.is_available()
+    return mcmil_b200
+
+
+def _bits(keep, dev):
+    return torch.from_numpy(PX.pack_bits(keep).view(np.int32)).to(dev)
+
+
+def _check(res, ref, impl, T, A_ref=None, A_stride=1):
+    """res: MCHeadResult for ONE bag; ref: dict with Y (T,C), prob_mean/m2, attn_mean/m2 (fp64-ish)."""
+    rel_mean, rel_m2, y_abs = REL[impl]
+    Y = res.Y[0].double().cpu().numpy()
+    assert np.isfinite(Y).all()
+    P = G.finish_stats(Y, np.zeros((T, Y.shape[1], 1)))["P"]
+    Pref = G.finish_stats(np.asarray(ref["Y"], np.float64), np.zeros((T, Y.shape[1], 1)))["P"]
+    assert np.abs(P / Pref - 1).max() < PROB_RTOL, "per-sample probabilities"
+    assert np.abs(Y - ref["Y"]).max() < y_abs * max(1.0, np.abs(ref["Y"]).max()), "per-sample logits"
+    pm = res.prob_mean[0].double().cpu().numpy()
+    assert np.abs(pm / ref["prob_mean"] - 1).max() < PROB_RTOL, "mean probability"
+    pq = res.prob_m2[0].double().cpu().numpy()
+    assert np.abs(pq - ref["prob_m2"]).max() < 1e-4 + 2e-2 * np.abs(ref["prob_m2"]).max()
+    am = res.attn_mean.double().cpu().numpy()
+    aq = res.attn_m2.double().cpu().numpy()
+    assert np.abs(am - ref["attn_mean"]).max() < ATTN_ATOL, "attention mean (abs)"
+    assert np.abs(aq / max(T - 1, 1) - ref["attn_m2"] / max(T - 1, 1)).max() < ATTN_ATOL, "attention variance (abs)"
+    assert np.abs(am / ref["attn_mean"] - 1).max() < rel_mean, "attention mean (rel)"
+    scale = np.abs(ref["attn_m2"]).max()
+    if T > 1 and scale > 0:
+        assert np.abs(aq - ref["attn_m2"]).max() < rel_m2 * scale, "attention M2 (rel to max)"
+    if A_ref is not None and res.A is not None:
+        A = res.A.double().cpu().numpy()[::A_stride]
+        assert np.abs(A - A_ref).max() < ATTN_ATOL
+        assert np.abs(A / A_ref - 1).max() < max(rel_mean * 3, 1e-4), "per-sample attention (rel)"
+
+
+def test_library_loaded_and_exports(mm):
+    from mcmil_b200 import _lib
+    lib = _lib.load()
+    for name in _lib.declared_symbols():
+        assert hasattr(lib, name)
+    assert lib.mcmil_version() >= 100
+
+
+def test_exported_masks_match_numpy_philox(mm):
+    dev = torch.device("cuda")
+    cu = np.array([0, 70, 71, 200], np.int32)
+    T, C, seed = 5, 3, 0x1234567890ABCDEF
+    fb, ab = mm.export_masks(T, cu, C, seed, 0.1, 0.25, t_offset=3, bag_offset=2, device=dev)
+    fb, ab = fb.cpu().numpy().view(np.uint32), ab.cpu().numpy().view(np.uint32)
+    for b in range(3):
+        n = cu[b + 1] - cu[b]
+        kf = PX.feature_keep(seed, 2 + b, 3, T, n, 0.1)
+        ka = PX.attn_keep(seed, 2 + b, 3, T, n, C, 0.25)
+        got_f = PX.unpack_bits(fb[:, cu[b]:cu[b + 1]], 512)
+        assert np.array_equal(got_f, kf)
+        got_a = PX.unpack_bits(ab, cu[-1])[:, :, cu[b]:cu[b + 1]]
+        assert np.array_equal(got_a, ka)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_injected_masks(mm, name, impl):
+    """Masks injected (Philox-regenerated, or the reference's own torch draws for *_native):
+    CUDA path vs the reference outputs stored in tests/golden/."""
+    c = Case(name)
+    dev = torch.device("cuda")
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in c.sd.items()}, dev)
+    H = torch.from_numpy(c.H).to(dev)
+    res = mm.mc_head(w, H, c.T, p_f=c.p_f, p_a=c.p_a, keep_f_bits=_bits(c.keep_f, dev),
+                     keep_a_bits=_bits(c.keep_a, dev), return_attention=True, impl=impl)
+    _check(res, c.ref, impl, c.T, A_ref=c.ref["A"].astype(np.float64), A_stride=c.A_stride)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.endswith("native")])
+def test_golden_inkernel_philox(mm, name, impl):
+    """Same cases with the masks drawn by the in-kernel Philox (no injection): must land on the
+    same reference outputs, because the golden masks ARE that Philox stream."""
+    c = Case(name)
+    dev = torch.device("cuda")
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in c.sd.items()}, dev)
+    H = torch.from_numpy(c.H).to(dev)
+    res = mm.mc_head(w, H, c.T, seed=c.mseed, p_f=c.p_f, p_a=c.p_a, t_offset=c.t0, bag_offset=c.bag,
+                     return_attention=True, impl=impl)
+    _check(res, c.ref, impl, c.T, A_ref=c.ref["A"].astype(np.float64), A_stride=c.A_stride)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("shared", [True, False])
+def test_ragged_batch_vs_oracle(mm, impl, shared):
+    """Packed variable-length batch (incl. a 1-patch bag and tile-boundary sizes) vs the fp64 oracle."""
+    dev = torch.device("cuda")
+    lens = [200, 77, 333, 1, 128, 129, 64]
+    ids = [5, 0, 9, 2, 3, 4, 11]
+    T, C, seed = 7, 2, 99
+    sd = G.make_weights(21, C, shared)
+    Hs = [G.make_features(300 + i, n) for i, n in enumerate(lens)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
+    res = mm.mc_head(w, torch.from_numpy(np.concatenate(Hs)).to(dev), T, seed=seed, cu_seqlens=cu, bag_ids=ids,
+                     t_offset=4, return_attention=True, impl=impl)
+    for b, n in enumerate(lens):
+        kf = PX.feature_keep(seed, ids[b], 4, T, n, 0.1)
+        ka = PX.attn_keep(seed, ids[b], 4, T, n, C, 0.1)
+        ref = G.mc_head_oracle(sd, Hs[b], kf, ka, 0.1, 0.1)
+        sl = slice(cu[b], cu[b + 1])
+        one = mm.MCHeadResult(res.Y[b:b + 1], res.prob_mean[b:b + 1], res.prob_m2[b:b + 1], res.attn_mean[:, sl],
+                              res.attn_m2[:, sl], res.A[:, :, sl], T, cu[b:b + 2] - cu[b])
+        _check(one, ref, impl, T, A_ref=ref["A"])
+
+
+@pytest.mark.parametrize("shared", [True, False])
+def test_config2_tcgen05_vs_fp32_and_properties(mm, shared):
+    """BASELINE config 2 (N=1024, T=100) at full size: tensor-core path vs the fp32 CUDA-core path
+    on the same Philox stream, plus size-independent properties."""
+    dev = torch.device("cuda")
+    N, T = 1024, 100
+    sd = G.make_weights(31, 2, shared)
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
+    H = torch.from_numpy(G.make_features(400, N)).to(dev)
+    a = mm.mc_head(w, H, T, seed=5, impl="tcgen05", return_attention=True)
+    b = mm.mc_head(w, H, T, seed=5, impl="simt_fp32", return_attention=True)
+    Pa, Pb = a.probs().double(), b.probs().double()
+    assert (Pa / Pb - 1).abs().max().item() < PROB_RTOL
+    assert (a.attn_mean - b.attn_mean).abs().max().item() < ATTN_ATOL
+    assert (a.attn_mean / b.attn_mean - 1).abs().max().item() < 3e-3
+    assert (a.attn_var() - b.attn_var()).abs().max().item() < ATTN_ATOL
+    assert (a.attn_m2 - b.attn_m2).abs().max().item() < 3e-2 * b.attn_m2.abs().max().item()
+    for r in (a, b):
+        assert (r.A.sum(-1) - 1).abs().max().item() < 1e-4          # every softmax row sums to one
+        assert (r.attn_mean.sum(-1) - 1).abs().max().item() < 1e-4
+        assert (r.prob_mean.sum(-1) - 1).abs().max().item() < 1e-5
+        assert (r.attn_m2 >= 0).all() and (r.prob_m2 >= 0).all()
+        # statistics are the statistics of the returned samples
+        assert (r.A.mean(0) - r.attn_mean).abs().max().item() < 1e-7
+        assert (r.A.var(0, unbiased=True) - r.attn_var(1)).abs().max().item() < 1e-9
+        assert (r.probs()[0].mean(0) - r.prob_mean[0]).abs().max().item() < 1e-6
+    # run-to-run determinism (no float atomics anywhere)
+    a2 = mm.mc_head(w, H, T, seed=5, impl="tcgen05", return_attention=True)
+    assert torch.equal(a.Y, a2.Y) and torch.equal(a.attn_m2, a2.attn_m2) and torch.equal(a.A, a2.A)
+    # a different seed gives different samples
+    a3 = mm.mc_head(w, H, T, seed=6, impl="tcgen05")
+    assert not torch.equal(a.Y, a3.Y)
+
+
+def test_sample_sharding_equals_single_call(mm):
+    """MC-sample split (config 4 mechanics on one GPU): two half-calls with t_offset + the additive
+    Welford merge reproduce the single call — masks are keyed by the global sample index."""
+    from mcmil_b200 import distributed as D
+    dev = torch.device("cuda")
+    N, T = 500, 40
+    sd = G.make_weights(41, 2, True)
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
+    H = torch.from_numpy(G.make_features(500, N)).to(dev)
+    full = mm.mc_head(w, H, T, seed=3)
+    packed = None
+    Ys = []
+    for r in range(4):
+        t0, Tl = D.mc_shard(T, r, 4)
+        part = mm.mc_head(w, H, Tl, seed=3, t_offset=t0)
+        Ys.append(part.Y)
+        pk = D.welford_pack(torch.cat([part.attn_mean.reshape(-1), part.prob_mean.reshape(-1)]),
+                            torch.cat([part.attn_m2.reshape(-1), part.prob_m2.reshape(-1)]), Tl)
+        packed = pk if packed is None else packed + pk
+    n = full.attn_mean.numel() + full.prob_mean.numel()
+    mean, m2 = D.welford_unpack(packed, n)
+    assert int(round(packed[0].item())) == T
+    assert torch.equal(torch.cat(Ys, dim=1), full.Y)
+    ref_mean = torch.cat([full.attn_mean.reshape(-1), full.prob_mean.reshape(-1)])
+    ref_m2 = torch.cat([full.attn_m2.reshape(-1), full.prob_m2.reshape(-1)])
+    assert (mean / ref_mean - 1).abs().max().item() < 1e-5
+    assert (m2 - ref_m2).abs().max().item() < 1e-3 * ref_m2.abs().max().item() + 1e-12
+
+
+def test_module_dropin_interface(mm):
+    """Same module surface as the reference: state_dict keys load, mc_inference returns the
+    (Y (T,1,C), A (T,1,C,N)) 2-tuple (model.py:328), statistics ride along."""
+    import torch.nn as nn
+    dev = torch.device("cuda")
+    for shared in (True, False):
+        sd = G.make_weights(51, 2, shared)
+        m = mm.MultiHeadGatedAttentionMIL(pretrained=False, shared_attention=shared)
+        head_keys = {k for k in m.state_dict() if not k.startswith("feature_extractor")}
+        assert head_keys == set(sd.keys())
+        m.feature_extractor = nn.Flatten()
+        missing, unexpected = m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+        assert not unexpected and not missing
+        N, T = 96, 9
+        Hn = G.make_features(600, N)
+        x = torch.from_numpy(Hn).view(1, N, 512, 1, 1)
+        Y, A = m.mc_inference(x, N=T, device="cuda", seed=77)
+        assert Y.shape == (T, 1, 2) and A.shape == (T, 1, 2, N) and Y.is_cuda
+        assert all(mod.training for mod in m.modules() if isinstance(mod, nn.Dropout))   # model.py:268-271
+        assert not m.training
+        ref = G.mc_head_oracle(sd, Hn, PX.feature_keep(77, 0, 0, T, N, 0.1), PX.attn_keep(77, 0, 0, T, N, 2, 0.1), 0.1, 0.1)
+        assert np.abs(A[:, 0].double().cpu().numpy() - ref["A"]).max() < ATTN_ATOL
+        P = torch.softmax(Y[:, 0].double(), -1).cpu().numpy()
+        assert np.abs(P / ref["P"] - 1).max() < PROB_RTOL
+        assert len(m.mc_inference(x, N=T, device="cuda", legacy_tuple=True)) == 3
+        assert m.last_result.count == T
+        with pytest.raises(RuntimeError):
+            m.mc_inference(torch.zeros(2, 4, 512, 1, 1), N=2, device="cuda")            # bs != 1, model.py:309
+
+
+def test_argument_errors(mm):
+    dev = torch.device("cuda")
+    sd = G.make_weights(1, 2, True)
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
+    H = torch.zeros(10, 512, device=dev)
+    with pytest.raises(RuntimeError):
+        mm.mc_head(w, H.cpu(), 3)
+    with pytest.raises(ValueError):
+        mm.mc_head(w, torch.zeros(10, 256, device=dev), 3)
+    with pytest.raises(ValueError):
+        mm.mc_head(w, H, 0)
+    with pytest.raises(ValueError):
+        mm.mc_head(w, H, 3, cu_seqlens=[0, 4, 4, 10])       # empty bag
+    with pytest.raises(ValueError):
+        mm.mc_head(w, H, 3, p_f=1.5)
+    with pytest.raises(ValueError):
+        mm.mc_head(w, H.double(), 3)
+    r = mm.mc_head(w, H, 3, p_f=1.0, p_a=1.0)                # nn.Dropout(p=1): everything dropped
+    assert torch.isfinite(r.Y).all() and (r.Y.abs().max().item() == 0.0)
+    assert (r.attn_mean - 0.1).abs().max().item() < 1e-6     # all logits 0 -> uniform attention

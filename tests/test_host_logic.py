@@ -1,0 +1,117 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/mcmil_b200.h declares (no
+compute calls without a GPU), host-side sharding logic, and the world_size-2 gloo path of the
+Welford merge."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from mcmil_b200 import _lib
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 12
+    assert set(declared) == set(_lib.SIGNATURES), "ctypes table and header disagree"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mcmil_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import mcmil_b200 as mm
+    with pytest.raises(RuntimeError):
+        mm.HeadWeights({}, device="cpu")
+    m = mm.MultiHeadGatedAttentionMIL(pretrained=False)
+    with pytest.raises(RuntimeError):
+        m.mc_inference(torch.zeros(1, 2, 3, 32, 32), N=2, device="cpu")
+
+
+def test_module_state_dict_matches_reference_schema():
+    import mcmil_b200 as mm
+    from oracle import gamil_oracle as G
+    for shared in (True, False):
+        m = mm.MultiHeadGatedAttentionMIL(pretrained=False, shared_attention=shared, num_classes=2)
+        head = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith("feature_extractor")}
+        want = {k: v.shape for k, v in G.make_weights(0, 2, shared).items()}
+        assert head == want
+        # torch forward (training path, not accelerated) keeps the reference's 3-tuple
+        m.feature_extractor = torch.nn.Flatten()
+        m.eval()
+        Y, A, aux = m(torch.rand(1, 6, 512, 1, 1))
+        assert Y.shape == (1, 2) and A.shape == (1, 2, 6) and aux is None
+
+
+def test_lpt_and_mc_shard():
+    from mcmil_b200 import distributed as D
+    rng = np.random.default_rng(0)
+    lens = rng.integers(200, 3001, 256)
+    for world in (1, 2, 4, 8):
+        parts = D.lpt_assign(lens, world)
+        assert sorted(i for p in parts for i in p) == list(range(256))
+        loads = [sum(-(-int(lens[i]) // 128) for i in p) for p in parts]
+        assert max(loads) - min(loads) <= 24          # one largest bag at most
+    for T, world in ((1000, 8), (100, 3), (7, 8), (5, 1)):
+        seen = []
+        for r in range(world):
+            t0, n = D.mc_shard(T, r, world)
+            seen += list(range(t0, t0 + n))
+        assert seen == list(range(T))
+
+
+def test_welford_pack_unpack_cpu():
+    from mcmil_b200 import distributed as D
+    rng = np.random.default_rng(1)
+    x = torch.from_numpy(rng.random((30, 50)) * 1e-3)
+    packed = None
+    for part in x.split(10):
+        mean = part.mean(0)
+        pk = D.welford_pack(mean.float(), ((part - mean) ** 2).sum(0).float(), part.shape[0])
+        packed = pk if packed is None else packed + pk
+    mean, m2 = D.welford_unpack(packed, 50)
+    assert torch.allclose(mean.double(), x.mean(0), rtol=1e-6)
+    assert torch.allclose(m2.double(), ((x - x.mean(0)) ** 2).sum(0), rtol=1e-4)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, T, n, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mcmil_b200 import distributed as D
+    rng = np.random.default_rng(123)                      # every rank builds the same population
+    x = torch.from_numpy(rng.random((T, n)) * 1e-3)
+    p = torch.from_numpy(rng.random((T, 2)))
+    t0, Tl = D.mc_shard(T, rank, world)
+    xs, ps = x[t0:t0 + Tl], p[t0:t0 + Tl]
+    (am, pm), (aq, pq), total = D.allreduce_welford(
+        [xs.mean(0).float(), ps.mean(0).float()],
+        [((xs - xs.mean(0)) ** 2).sum(0).float(), ((ps - ps.mean(0)) ** 2).sum(0).float()], Tl)
+    ok = (total == T
+          and torch.allclose(am.double(), x.mean(0), rtol=1e-5)
+          and torch.allclose(aq.double(), ((x - x.mean(0)) ** 2).sum(0), rtol=1e-3)
+          and torch.allclose(pm.double(), p.mean(0), rtol=1e-5)
+          and torch.allclose(pq.double(), ((p - p.mean(0)) ** 2).sum(0), rtol=1e-3))
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_allreduce_welford_gloo_world2():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, 101, 333, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
