@@ -38,6 +38,8 @@ class HeadWeights:
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("the MC-dropout head runs on CUDA only (no CPU fallback)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         sd = {k: v for k, v in state_dict.items() if not k.startswith("feature_extractor")}
         C_ = 0
         while f"classifiers.{C_}.weight" in sd:
@@ -239,6 +241,8 @@ def export_masks(T: int, R_or_cu, num_classes: int, seed: int, p_f: float, p_a: 
     """The keep-bits the in-kernel Philox draws: (feat (T,R,16) int32, attn (T,C,ceil(R/32)) int32)."""
     lib = _lib.load()
     dev = torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
     cu = np.array([0, int(R_or_cu)], np.int32) if np.isscalar(R_or_cu) else np.asarray(R_or_cu, np.int32)
     plan = _get_plan(cu, T, num_classes, dev)
     R = plan.R
