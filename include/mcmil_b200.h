@@ -127,6 +127,13 @@ int mcmil_debug_proj_tc(const mcmil_weights_t* w, const mcmil_plan_t* plan, cons
                         float* dbg, float* logits_out, float* scores_out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- measurement hook (bench.py): brackets the tcgen05 projection launch(es) of the next
+ * `max_calls` mcmil_head_forward calls with CUDA events on the launching stream;
+ * mcmil_profile_end synchronises them and returns the summed device time and the number of
+ * projection kernels covered.  Not thread-safe; off by default. */
+int mcmil_profile_begin(int max_calls);
+int mcmil_profile_end(double* total_ms, int* kernels);
+
 /* number of kernels the last mcmil_head_forward on this thread launched (bench "gpu_launches") */
 int mcmil_last_launch_count(void);
 

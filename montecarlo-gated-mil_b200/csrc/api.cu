@@ -15,6 +15,14 @@ namespace {
 thread_local std::string g_err;
 thread_local int g_launches = 0;
 
+// optional CUDA-event bracketing of the projection kernel(s), for bench.py's roofline figure
+struct Profile {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  size_t used = 0;       // events recorded so far (pairs * 2)
+  int kernels = 0;       // projection launches covered
+} g_prof;
+
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 int cuda_fail(cudaError_t e, const char* where) {
   g_err = std::string(where) + ": " + cudaGetErrorString(e);
@@ -173,7 +181,10 @@ int mcmil_head_forward(const mcmil_weights_t* w, const mcmil_plan_t* plan, const
     e = launch_pack_h16(*plan, H, h16, st, &g_launches);
     if (e != cudaSuccess) return cuda_fail(e, "pack_h16");
     // MCMIL_DEBUG_DUMP: prob_m2 doubles as nothing — debug dumps go through mcmil_debug_forward
+    const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
+    if (prof) cudaEventRecord(g_prof.ev[g_prof.used], st);
     e = launch_proj_tc(*w, *plan, m, h16, logits, scores, nullptr, st, &g_launches);
+    if (prof) { cudaEventRecord(g_prof.ev[g_prof.used + 1], st); g_prof.used += 2; g_prof.kernels += w->S; }
     if (e != cudaSuccess) return cuda_fail(e, "proj_tc");
   } else if (impl == MCMIL_IMPL_SIMT_FP32) {
     e = launch_proj_simt(*w, *plan, m, H, logits, scores, st, &g_launches);
@@ -206,6 +217,33 @@ int mcmil_debug_proj_tc(const mcmil_weights_t* w, const mcmil_plan_t* plan, cons
   if (e == cudaSuccess && logits_out) e = cudaMemcpyAsync(logits_out, logits, plane, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess && scores_out) e = cudaMemcpyAsync(scores_out, scores, plane, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "mcmil_debug_proj_tc");
+  return 0;
+}
+
+int mcmil_profile_begin(int max_calls) {
+  if (max_calls < 1) return fail(MCMIL_E_BADARG, "mcmil_profile_begin: max_calls must be >= 1");
+  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+  g_prof.ev.assign((size_t)max_calls * 2, nullptr);
+  for (auto& e : g_prof.ev) {
+    cudaError_t err = cudaEventCreate(&e);
+    if (err != cudaSuccess) return cuda_fail(err, "mcmil_profile_begin");
+  }
+  g_prof.used = 0; g_prof.kernels = 0; g_prof.on = true;
+  return 0;
+}
+int mcmil_profile_end(double* total_ms, int* kernels) {
+  if (!total_ms || !kernels) return fail(MCMIL_E_BADARG, "mcmil_profile_end: null pointer");
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    cudaError_t err = cudaEventSynchronize(g_prof.ev[i + 1]);
+    float ms = 0.f;
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]);
+    if (err != cudaSuccess) return cuda_fail(err, "mcmil_profile_end");
+    total += ms;
+  }
+  *total_ms = total; *kernels = g_prof.kernels;
+  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+  g_prof.ev.clear(); g_prof.used = 0; g_prof.on = false;
   return 0;
 }
 
