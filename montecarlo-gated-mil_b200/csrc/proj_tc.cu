@@ -108,7 +108,7 @@ __device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tcol
   }
 }
 
-template <int NOUT>
+template <int NOUT, bool INJECT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 proj_tc_kernel(const __grid_constant__ ProjParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -166,33 +166,46 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       }
     }
   } else if (warp == MMA_WARP) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA, one thread)
-    if (rank == 0 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    // The whole warp runs the loop so that every address / descriptor stays in uniform registers;
+    // one elected lane issues the tcgen05 instructions (a lane-0-only loop makes ptxas emit
+    // ELECT + R2UR chains per MMA and the issue thread becomes the bottleneck, profiles/r1).
+    if (rank == 0) {
       constexpr uint32_t IDESC_MAIN = umma_idesc_f16(128, 256);
       constexpr uint32_t IDESC_SCORE = umma_idesc_f16(128, 16);
       mbar_wait(bar_addr(sbase, B_WREADY), 0);
       tc_fence_after();
-      uint32_t k = 0, tc = 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint64_t adesc0 = umma_desc_sw128(sbase + SM_RING);
+      const uint64_t bdesc0 = umma_desc_sw128(sbase + SM_W);
+      const uint64_t sdesc0 = umma_desc_sw128(sbase + SM_WS);
+      uint32_t stage = 0, phase = 0, tc = 0;
       for (long long u = u_begin; u < u_end; ++u, ++tc) {
         const uint32_t buf = tc & 1;
         mbar_wait(bar_addr(sbase, B_TEMPTY + buf), ((tc >> 1) & 1) ^ 1);
         tc_fence_after();
-        for (int s = 0; s < NSLICE; ++s, ++k) {
-          const uint32_t stage = k % NUM_STAGES, use = k / NUM_STAGES;
-          mbar_wait(bar_addr(sbase, B_FULL + stage), use & 1);
+        const uint32_t dmain = tmem_u + TM_MAIN + buf * 128, dscore = tmem_u + TM_SCORE + buf * 32;
+#pragma unroll 1
+        for (int s = 0; s < NSLICE; ++s) {
+          mbar_wait(bar_addr(sbase, B_FULL + stage), phase);
           tc_fence_after();
-          const uint32_t a0 = sbase + SM_RING + stage * SLICE_BYTES_A;
-          const uint32_t b0 = sbase + SM_W + s * SLICE_BYTES_W;
-          const uint32_t s0 = sbase + SM_WS + s * SLICE_BYTES_S;
+          if (elect_one()) {
+            // start-address field is (addr >> 4): advancing by bytes/16 stays inside the 14-bit field
+            const uint64_t ad = adesc0 + (uint64_t)(stage * (SLICE_BYTES_A >> 4));
+            const uint64_t bd = bdesc0 + (uint64_t)(s * (SLICE_BYTES_W >> 4));
+            const uint64_t sd = sdesc0 + (uint64_t)(s * (SLICE_BYTES_S >> 4));
 #pragma unroll
-          for (int kk = 0; kk < KSLICE / 16; ++kk) {
-            const uint64_t ad = umma_desc_sw128(a0 + kk * 32);
-            umma_f16_cg2(tmem_base + TM_MAIN + buf * 128, ad, umma_desc_sw128(b0 + kk * 32), IDESC_MAIN, (s | kk) != 0);
-            umma_f16_cg2(tmem_base + TM_SCORE + buf * 32, ad, umma_desc_sw128(s0 + kk * 32), IDESC_SCORE, (s | kk) != 0);
+            for (int kk = 0; kk < KSLICE / 16; ++kk) {
+              umma_f16_cg2(dmain, ad + 2 * kk, bd + 2 * kk, IDESC_MAIN, (s | kk) != 0);
+              umma_f16_cg2(dscore, ad + 2 * kk, sd + 2 * kk, IDESC_SCORE, (s | kk) != 0);
+            }
+            umma_commit_cg2_mc(bar_addr(sbase, B_EMPTY + stage), 3);
           }
-          umma_commit_cg2_mc(bar_addr(sbase, B_EMPTY + stage), 3);
+          __syncwarp();
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_cg2_mc(bar_addr(sbase, B_TFULL + buf), 3);
+        if (elect_one()) umma_commit_cg2_mc(bar_addr(sbase, B_TFULL + buf), 3);
+        __syncwarp();
       }
     }
   } else if (warp >= PRODUCER_WARP0) {
@@ -207,7 +220,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       rowi[i] = pw * 8 + i * 4 + (lane >> 3);
       off[i] = (uint32_t)rowi[i] * 128u + (uint32_t)((chunk ^ (rowi[i] & 7)) << 4);
     }
-    uint32_t k = 0;
+    uint32_t stage = 0, phase = 0;      // ring position of the next slice this warp fills
     int it = 0;
     for (long long u = u_begin; u < u_end; ++it) {
       const int ti = (int)(u / P.T);
@@ -217,36 +230,61 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       const TileDesc td = P.tiles[ti];
       mbar_wait(bar_addr(sbase, B_HFULL), (uint32_t)(it & 1));
       const uint32_t bag = (uint32_t)(P.bag_offset + td.gbag);
+      uint32_t nrow[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) nrow[i] = (uint32_t)(td.n0 + (int)rank * HALF_ROWS + rowi[i]);
+#pragma unroll 1
       for (int t = t_begin; t < t_end; ++t) {
         const uint32_t tg = (uint32_t)(P.t_offset + t);
-        for (int s = 0; s < NSLICE; ++s, ++k) {
-          const uint32_t stage = k % NUM_STAGES, use = k / NUM_STAGES;
-          mbar_wait(bar_addr(sbase, B_EMPTY + stage), (use & 1) ^ 1);
+#pragma unroll 1
+        for (int sp = 0; sp < NSLICE; sp += 2) {
+          // masks of two K-slices x two chunks: four independent Philox chains per thread (ILP),
+          // drawn before the ring slot is known to be free
+          uint4 rnd[2][2];
+          if constexpr (!INJECT) {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const uint4 h = *reinterpret_cast<const uint4*>(smem + SM_H + s * SLICE_BYTES_A + off[i]);
-            uint4 o;
-            if (P.inj_feat == nullptr) {
-              const uint4 r = philox4x32((uint32_t)(s * 8 + chunk), (uint32_t)(td.n0 + (int)rank * HALF_ROWS + rowi[i]), tg, bag, P.key);
-              o.x = h.x & keep_mask2(r.x, thr2);
-              o.y = h.y & keep_mask2(r.y, thr2);
-              o.z = h.z & keep_mask2(r.z, thr2);
-              o.w = h.w & keep_mask2(r.w, thr2);
-            } else {
-              const int trow = (int)rank * HALF_ROWS + rowi[i];
-              uint32_t bits = 0;
-              if (trow < td.nrows)
-                bits = reinterpret_cast<const uint8_t*>(P.inj_feat)[((size_t)t * P.R + td.row0 + trow) * 64 + s * 8 + chunk];
-              o.x = h.x & ((bits & 1u ? 0x0000FFFFu : 0u) | (bits & 2u ? 0xFFFF0000u : 0u));
-              o.y = h.y & ((bits & 4u ? 0x0000FFFFu : 0u) | (bits & 8u ? 0xFFFF0000u : 0u));
-              o.z = h.z & ((bits & 16u ? 0x0000FFFFu : 0u) | (bits & 32u ? 0xFFFF0000u : 0u));
-              o.w = h.w & ((bits & 64u ? 0x0000FFFFu : 0u) | (bits & 128u ? 0xFFFF0000u : 0u));
-            }
-            *reinterpret_cast<uint4*>(smem + SM_RING + stage * SLICE_BYTES_A + off[i]) = o;
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+                rnd[j][i] = philox4x32((uint32_t)((sp + j) * 8 + chunk), nrow[i], tg, bag, P.key);
+            // keep the four chains ahead of the (volatile) barrier polls below: ptxas otherwise sinks
+            // the arithmetic behind the wait and serialises RNG latency with the ring hand-shake
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+                asm volatile("" : "+r"(rnd[j][i].x), "+r"(rnd[j][i].y), "+r"(rnd[j][i].z), "+r"(rnd[j][i].w));
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(full_leader + stage * 8);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int s = sp + j;
+            mbar_wait(bar_addr(sbase, B_EMPTY + stage), phase ^ 1);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint4 h = *reinterpret_cast<const uint4*>(smem + SM_H + s * SLICE_BYTES_A + off[i]);
+              uint4 o;
+              if constexpr (!INJECT) {
+                o.x = h.x & keep_mask2(rnd[j][i].x, thr2);
+                o.y = h.y & keep_mask2(rnd[j][i].y, thr2);
+                o.z = h.z & keep_mask2(rnd[j][i].z, thr2);
+                o.w = h.w & keep_mask2(rnd[j][i].w, thr2);
+              } else {
+                const int trow = (int)rank * HALF_ROWS + rowi[i];
+                uint32_t bits = 0;
+                if (trow < td.nrows)
+                  bits = reinterpret_cast<const uint8_t*>(P.inj_feat)[((size_t)t * P.R + td.row0 + trow) * 64 + s * 8 + chunk];
+                o.x = h.x & ((bits & 1u ? 0x0000FFFFu : 0u) | (bits & 2u ? 0xFFFF0000u : 0u));
+                o.y = h.y & ((bits & 4u ? 0x0000FFFFu : 0u) | (bits & 8u ? 0xFFFF0000u : 0u));
+                o.z = h.z & ((bits & 16u ? 0x0000FFFFu : 0u) | (bits & 32u ? 0xFFFF0000u : 0u));
+                o.w = h.w & ((bits & 64u ? 0x0000FFFFu : 0u) | (bits & 128u ? 0xFFFF0000u : 0u));
+              }
+              *reinterpret_cast<uint4*>(smem + SM_RING + stage * SLICE_BYTES_A + off[i]) = o;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(full_leader + stage * 8);
+            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
       __syncwarp();
@@ -299,7 +337,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         if (half == 0 && valid) {
           const uint32_t tg = (uint32_t)(P.t_offset + t);
           uint4 rnd = make_uint4(0, 0, 0, 0);
-          if (P.inj_attn == nullptr)
+          if constexpr (!INJECT)
             rnd = attn_words(0u, (uint32_t)(td.n0 + trow), tg, (uint32_t)(P.bag_offset + td.gbag), P.key);
 #pragma unroll
           for (int c = 0; c < NOUT; ++c) {
@@ -307,7 +345,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
               const int head = P.head0 + c;
               float logit = acc[c] + x[c] + P.epi.bw[c];
               bool keep;
-              if (P.inj_attn == nullptr) keep = attn_keep_from(rnd, head, P.thr_a);
+              if constexpr (!INJECT) keep = attn_keep_from(rnd, head, P.thr_a);
               else keep = (P.inj_attn[((size_t)t * P.C + head) * (P.Rp >> 5) + (g >> 5)] >> (g & 31)) & 1u;
               logit = keep ? logit * P.sa : 0.f;           // a dropped logit is 0, not -inf (model.py:291,305)
               const size_t o = ((size_t)t * P.C + head) * P.Rp + g;
@@ -333,13 +371,17 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 
 cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const uint8_t* h16,
                            float* logits, float* scores, float* dbg, cudaStream_t st, int* launches) {
+  using KernelFn = void (*)(ProjParams);
+  static const KernelFn kernels[2][4] = {
+      {proj_tc_kernel<1, false>, proj_tc_kernel<2, false>, proj_tc_kernel<3, false>, proj_tc_kernel<4, false>},
+      {proj_tc_kernel<1, true>, proj_tc_kernel<2, true>, proj_tc_kernel<3, true>, proj_tc_kernel<4, true>}};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(proj_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(proj_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(proj_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(proj_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
-    if (e != cudaSuccess) return e;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 4; ++b) {
+        cudaError_t e = cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+        if (e != cudaSuccess) return e;
+      }
     attr_set = true;
   }
   int dev = 0, sms = 0;
@@ -366,12 +408,7 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
     P.sf = m.sf; P.hsf = 0.5f * m.sf; P.sa = m.sa;
     P.key = m.key;
     P.epi = w.epi[s];
-    switch (P.n_out) {
-      case 1: proj_tc_kernel<1><<<2 * n_pairs, TC_THREADS, SM_TOTAL, st>>>(P); break;
-      case 2: proj_tc_kernel<2><<<2 * n_pairs, TC_THREADS, SM_TOTAL, st>>>(P); break;
-      case 3: proj_tc_kernel<3><<<2 * n_pairs, TC_THREADS, SM_TOTAL, st>>>(P); break;
-      default: proj_tc_kernel<4><<<2 * n_pairs, TC_THREADS, SM_TOTAL, st>>>(P); break;
-    }
+    kernels[m.inj_feat != nullptr ? 1 : 0][P.n_out - 1]<<<2 * n_pairs, TC_THREADS, SM_TOTAL, st>>>(P);
     if (launches) ++*launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
