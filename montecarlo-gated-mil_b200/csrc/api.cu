@@ -69,7 +69,6 @@ int mcmil_weights_create(mcmil_weights_t** out, int num_classes, int shared_atte
   cudaError_t e = cudaSuccess;
   const int S = w->S, C = w->C;
   if (e == cudaSuccess) e = dmalloc(&w->d_wmain, (size_t)S * 2 * NSLICE * SLICE_BYTES_W);
-  if (e == cudaSuccess) e = dmalloc(&w->d_wscore, (size_t)S * 2 * NSLICE * SLICE_BYTES_S);
   if (e == cudaSuccess) e = dmalloc(&w->d_wt, (size_t)S * L * 256);
   if (e == cudaSuccess) e = dmalloc(&w->d_bv, (size_t)S * D);
   if (e == cudaSuccess) e = dmalloc(&w->d_bu, (size_t)S * D);
@@ -85,7 +84,7 @@ int mcmil_weights_create(mcmil_weights_t** out, int num_classes, int shared_atte
 
 int mcmil_weights_destroy(mcmil_weights_t* w) {
   if (!w) return 0;
-  cudaFree(w->d_wmain); cudaFree(w->d_wscore); cudaFree(w->d_wt); cudaFree(w->d_bv); cudaFree(w->d_bu);
+  cudaFree(w->d_wmain); cudaFree(w->d_wt); cudaFree(w->d_bv); cudaFree(w->d_bu);
   cudaFree(w->d_ww); cudaFree(w->d_bw); cudaFree(w->d_cls);
   delete w;
   return 0;

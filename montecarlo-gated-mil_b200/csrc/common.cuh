@@ -16,8 +16,12 @@ constexpr int HALF_ROWS = 64;
 constexpr int KSLICE = 64;            // fp16 elements per 128-byte swizzle row
 constexpr int NSLICE = L / KSLICE;    // 8 K-slices
 constexpr int SLICE_BYTES_A = HALF_ROWS * 128;   // 8 KB : 64 rows x 128 B
-constexpr int SLICE_BYTES_W = 128 * 128;         // 16 KB: 128 W-rows x 128 B
-constexpr int SLICE_BYTES_S = 8 * 128;           // 1 KB : 8 score rows x 128 B
+// W slice of one CTA: 136 rows x 128 B.  rows [0,72) feed MMA "a" (N=144 over the pair):
+// 32 tanh rows, the matching 32 sigmoid rows, 8 classifier-score rows; rows [72,136) feed MMA "b"
+// (N=128): 32 tanh + 32 sigmoid rows of the upper hidden units.  (A separate N=16 score MMA costs
+// ~48 tensor-pipe cycles per K=16 step instead of the 4 the math needs: profiles/r1.)
+constexpr int W_ROWS_A = 72, W_ROWS_B = 64, W_ROWS = W_ROWS_A + W_ROWS_B;
+constexpr int SLICE_BYTES_W = W_ROWS * 128;      // 17 KB
 constexpr int TILE_H16_BYTES = 2 * NSLICE * SLICE_BYTES_A;  // 128 KB per pair tile
 
 // One pair tile = up to 128 consecutive patches of one bag.

@@ -10,9 +10,8 @@ struct Weights {
   int C = 0;            // num_classes
   int shared = 1;
   int S = 1;            // number of (V,U) parameter sets
-  // tcgen05 images, per set: [2 ranks][8 slices][16 KB] and [2 ranks][8 slices][1 KB]
+  // tcgen05 image, per set: [2 ranks][8 slices][136 rows x 128 B]
   uint8_t* d_wmain = nullptr;
-  uint8_t* d_wscore = nullptr;
   // fp32 copies for the SIMT path: WT [S][512][256] (k-major; cols 0..127 V, 128..255 U)
   float* d_wt = nullptr;
   float* d_bv = nullptr;   // [S][128]

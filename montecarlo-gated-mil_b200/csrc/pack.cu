@@ -13,44 +13,39 @@ __host__ __device__ inline uint32_t sw128_off(int r, int k) {
 }
 
 // ------------------------------------------------------------------ weights
-// main image: [S][2 ranks][8 slices][128 rows][128 B]; rank r row j: j<64 -> V row d=64r+j, else U row d=64r+j-64
-__global__ void pack_wmain_kernel(const float* __restrict__ V, const float* __restrict__ U, int S,
+// W image: [S][2 ranks][8 slices][136 rows][128 B] (row roles: common.cuh).  rank r, row j:
+//   j <  32: tanh row    d = 32 r + j            32 <= j <  64: sigmoid row d = 32 r + (j - 32)
+//   64 <= j < 72: classifier-score rows (rank 0 only; rows 0..3 = fp16 hi part, 4..7 = fp16(w - hi);
+//                 shared: slot i <-> head i, separate set s: slot 0 <-> head s), rank 1: zeros
+//   72 <= j < 104: tanh row d = 64 + 32 r + (j - 72)     104 <= j < 136: sigmoid row d = 64 + 32 r + (j - 104)
+__global__ void pack_wmain_kernel(const float* __restrict__ V, const float* __restrict__ U,
+                                  const float* __restrict__ cls, int S, int C, int shared,
                                   __half* __restrict__ img) {
-  const int total = S * 2 * NSLICE * 128 * KSLICE;
+  const int total = S * 2 * NSLICE * W_ROWS * KSLICE;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int kk = i % KSLICE;
-    const int j = (i / KSLICE) % 128;
-    const int q = (i / (KSLICE * 128)) % NSLICE;
-    const int r = (i / (KSLICE * 128 * NSLICE)) % 2;
-    const int s = i / (KSLICE * 128 * NSLICE * 2);
-    const int d = 64 * r + (j & 63);
-    const float* src = (j < 64 ? V : U) + ((size_t)s * D + d) * L + q * KSLICE + kk;
-    const size_t base = ((size_t)(s * 2 + r) * NSLICE + q) * SLICE_BYTES_W;
-    *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(img) + base + sw128_off(j, kk)) = __float2half_rn(*src);
-  }
-}
-
-// score image: [S][2 ranks][8 slices][8 rows][128 B]; rank 0 rows 0..3 = hi(fp16) of classifier rows,
-// rows 4..7 = lo = fp16(w - hi); rank 1 all zero.  shared: row i <-> head i; separate set s: row 0 <-> head s.
-__global__ void pack_wscore_kernel(const float* __restrict__ cls, int S, int C, int shared,
-                                   __half* __restrict__ img) {
-  const int total = S * 2 * NSLICE * 8 * KSLICE;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int kk = i % KSLICE;
-    const int row = (i / KSLICE) % 8;
-    const int q = (i / (KSLICE * 8)) % NSLICE;
-    const int r = (i / (KSLICE * 8 * NSLICE)) % 2;
-    const int s = i / (KSLICE * 8 * NSLICE * 2);
+    const int j = (i / KSLICE) % W_ROWS;
+    const int q = (i / (KSLICE * W_ROWS)) % NSLICE;
+    const int r = (i / (KSLICE * W_ROWS * NSLICE)) % 2;
+    const int s = i / (KSLICE * W_ROWS * NSLICE * 2);
+    const int k = q * KSLICE + kk;
     float v = 0.f;
-    const int slot = row & 3;
-    const int head = shared ? slot : (slot == 0 ? s : -1);
-    if (r == 0 && head >= 0 && head < C) {
-      const float w = cls[(size_t)head * L + q * KSLICE + kk];
-      const float hi = __half2float(__float2half_rn(w));
-      v = (row < 4) ? hi : (w - hi);
+    if (j < 64) {
+      v = (j < 32 ? V : U)[((size_t)s * D + 32 * r + (j & 31)) * L + k];
+    } else if (j < W_ROWS_A) {
+      const int row = j - 64, slot = row & 3;
+      const int head = shared ? slot : (slot == 0 ? s : -1);
+      if (r == 0 && head >= 0 && head < C) {
+        const float w = cls[(size_t)head * L + k];
+        const float hi = __half2float(__float2half_rn(w));
+        v = (row < 4) ? hi : (w - hi);
+      }
+    } else {
+      const int jj = j - W_ROWS_A;
+      v = (jj < 32 ? V : U)[((size_t)s * D + 64 + 32 * r + (jj & 31)) * L + k];
     }
-    const size_t base = ((size_t)(s * 2 + r) * NSLICE + q) * SLICE_BYTES_S;
-    *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(img) + base + sw128_off(row, kk)) = __float2half_rn(v);
+    const size_t base = ((size_t)(s * 2 + r) * NSLICE + q) * SLICE_BYTES_W;
+    *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(img) + base + sw128_off(j, kk)) = __float2half_rn(v);
   }
 }
 
@@ -68,8 +63,7 @@ cudaError_t launch_pack_weights(Weights& w, const float* attV_w, const float* at
                                 const float* attU_b, const float* attw_w, const float* attw_b,
                                 const float* cls_w, cudaStream_t st) {
   const int S = w.S, C = w.C;
-  pack_wmain_kernel<<<256, 256, 0, st>>>(attV_w, attU_w, S, reinterpret_cast<__half*>(w.d_wmain));
-  pack_wscore_kernel<<<64, 256, 0, st>>>(cls_w, S, C, w.shared, reinterpret_cast<__half*>(w.d_wscore));
+  pack_wmain_kernel<<<256, 256, 0, st>>>(attV_w, attU_w, cls_w, S, C, w.shared, reinterpret_cast<__half*>(w.d_wmain));
   pack_wt_kernel<<<256, 256, 0, st>>>(attV_w, attU_w, S, w.d_wt);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

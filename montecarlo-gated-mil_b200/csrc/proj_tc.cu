@@ -26,8 +26,7 @@ constexpr int NUM_STAGES = 3;
 constexpr int PRODUCER_WARP0 = 4, NUM_PRODUCER_WARPS = 8, MMA_WARP = 12, LOAD_WARP = 13;
 
 constexpr uint32_t SM_W = 0;
-constexpr uint32_t SM_WS = SM_W + NSLICE * SLICE_BYTES_W;          // 131072
-constexpr uint32_t SM_H = SM_WS + NSLICE * SLICE_BYTES_S;          // 139264
+constexpr uint32_t SM_H = SM_W + NSLICE * SLICE_BYTES_W;           // 139264
 constexpr uint32_t SM_RING = SM_H + NSLICE * SLICE_BYTES_A;        // 204800
 constexpr uint32_t SM_XCH = SM_RING + NUM_STAGES * SLICE_BYTES_A;  // 229376  [2][64][4] floats
 constexpr uint32_t SM_BAR = SM_XCH + 2 * HALF_ROWS * MAXC * 4;     // 231424
@@ -47,14 +46,16 @@ enum : uint32_t {
   TMEM_SLOT = 30               // uint32 at SM_BAR + 8*30
 };
 
+// TMEM columns of one accumulator buffer (2x2 layout of the pair MMAs: lanes 0..63 hold the
+// columns fed by the leader CTA's W rows, lanes 64..127 those of the peer CTA's W rows):
+//   [0,72)   MMA "a" (N=144): 32 tanh | 32 sigmoid | 8 score columns
+//   [96,160) MMA "b" (N=128): 32 tanh | 32 sigmoid of hidden units 64..127
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TM_MAIN = 0;      // 2 buffers x 128 columns (2x2 layout of an M=128,N=256 pair MMA)
-constexpr uint32_t TM_SCORE = 256;   // 2 buffers x 32 columns (8 used)
+constexpr uint32_t TM_A = 0, TM_B = 96, TM_BUF_STRIDE = 160;
 
 struct ProjParams {
   const uint8_t* h16;      // [n_tiles][2][8][8 KB]
-  const uint8_t* wmain;    // this set: [2][8][16 KB]
-  const uint8_t* wscore;   // this set: [2][8][1 KB]
+  const uint8_t* wmain;    // this set: [2][8][17 KB]
   const TileDesc* tiles;
   float* logits;           // [T][C][Rp]
   float* scores;           // [T][C][Rp]
@@ -84,26 +85,33 @@ __device__ __forceinline__ uint32_t keep_mask2(uint32_t r, uint32_t thr2) {
 }
 
 template <int HALF, int NOUT>
-__device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tcol, float (&acc)[MAXC],
+__device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tbuf, float (&acc)[MAXC],
                                               float* dbg_row) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint32_t v[16], u[16];
-    tmem_ld16(tcol + 16 * j, v);
-    tmem_ld16(tcol + 64 + 16 * j, u);
-    tmem_ld_wait();
-    if (dbg_row) {
+  for (int part = 0; part < 2; ++part) {            // MMA "a" columns, then MMA "b" columns
+    const uint32_t tcol = tbuf + (part == 0 ? TM_A : TM_B);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { dbg_row[16 * j + i] = __uint_as_float(v[i]); dbg_row[64 + 16 * j + i] = __uint_as_float(u[i]); }
-    }
+    for (int j = 0; j < 2; ++j) {
+      uint32_t v[16], u[16];
+      tmem_ld16(tcol + 16 * j, v);
+      tmem_ld16(tcol + 32 + 16 * j, u);
+      tmem_ld_wait();
+      if (dbg_row) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int d = 64 * HALF + 16 * j + i;
-      const float av = tanh_approx(fmaf(__uint_as_float(v[i]), P.sf, P.epi.bv[d]));
-      const float au = tanh_approx(fmaf(__uint_as_float(u[i]), P.hsf, P.epi.hbu[d]));
-      const float g2 = fmaf(av, au, av);            // 2 * tanh(.) * sigmoid(.)
+        for (int i = 0; i < 16; ++i) {
+          dbg_row[64 * part + 16 * j + i] = __uint_as_float(v[i]);
+          dbg_row[64 * part + 32 + 16 * j + i] = __uint_as_float(u[i]);
+        }
+      }
 #pragma unroll
-      for (int c = 0; c < NOUT; ++c) acc[c] = fmaf(g2, P.epi.hw[c][d], acc[c]);
+      for (int i = 0; i < 16; ++i) {
+        const int d = 64 * part + 32 * HALF + 16 * j + i;
+        const float av = tanh_approx(fmaf(__uint_as_float(v[i]), P.sf, P.epi.bv[d]));
+        const float au = tanh_approx(fmaf(__uint_as_float(u[i]), P.hsf, P.epi.hbu[d]));
+        const float g2 = fmaf(av, au, av);            // 2 * tanh(.) * sigmoid(.)
+#pragma unroll
+        for (int c = 0; c < NOUT; ++c) acc[c] = fmaf(g2, P.epi.hw[c][d], acc[c]);
+      }
     }
   }
 }
@@ -145,11 +153,9 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     // ------------------------------------------------------------ TMA loader
     if (lane == 0) {
       const uint32_t wloc = bar_addr(sbase, B_WLOC);
-      mbar_expect_tx(wloc, NSLICE * (SLICE_BYTES_W + SLICE_BYTES_S));
+      mbar_expect_tx(wloc, NSLICE * SLICE_BYTES_W);
       for (int s = 0; s < NSLICE; ++s)
         bulk_g2s(sbase + SM_W + s * SLICE_BYTES_W, P.wmain + (size_t)(rank * NSLICE + s) * SLICE_BYTES_W, SLICE_BYTES_W, wloc);
-      for (int s = 0; s < NSLICE; ++s)
-        bulk_g2s(sbase + SM_WS + s * SLICE_BYTES_S, P.wscore + (size_t)(rank * NSLICE + s) * SLICE_BYTES_S, SLICE_BYTES_S, wloc);
       mbar_wait(wloc, 0);
       mbar_arrive_cluster(mapa(bar_addr(sbase, B_WREADY), 0));
       const uint32_t hfull = bar_addr(sbase, B_HFULL), hempty = bar_addr(sbase, B_HEMPTY);
@@ -171,20 +177,19 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     // one elected lane issues the tcgen05 instructions (a lane-0-only loop makes ptxas emit
     // ELECT + R2UR chains per MMA and the issue thread becomes the bottleneck, profiles/r1).
     if (rank == 0) {
-      constexpr uint32_t IDESC_MAIN = umma_idesc_f16(128, 256);
-      constexpr uint32_t IDESC_SCORE = umma_idesc_f16(128, 16);
+      constexpr uint32_t IDESC_A = umma_idesc_f16(128, 2 * W_ROWS_A);
+      constexpr uint32_t IDESC_B = umma_idesc_f16(128, 2 * W_ROWS_B);
       mbar_wait(bar_addr(sbase, B_WREADY), 0);
       tc_fence_after();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t adesc0 = umma_desc_sw128(sbase + SM_RING);
       const uint64_t bdesc0 = umma_desc_sw128(sbase + SM_W);
-      const uint64_t sdesc0 = umma_desc_sw128(sbase + SM_WS);
       uint32_t stage = 0, phase = 0, tc = 0;
       for (long long u = u_begin; u < u_end; ++u, ++tc) {
         const uint32_t buf = tc & 1;
         mbar_wait(bar_addr(sbase, B_TEMPTY + buf), ((tc >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t dmain = tmem_u + TM_MAIN + buf * 128, dscore = tmem_u + TM_SCORE + buf * 32;
+        const uint32_t da = tmem_u + buf * TM_BUF_STRIDE + TM_A, db = tmem_u + buf * TM_BUF_STRIDE + TM_B;
 #pragma unroll 1
         for (int s = 0; s < NSLICE; ++s) {
           mbar_wait(bar_addr(sbase, B_FULL + stage), phase);
@@ -193,11 +198,10 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
             // start-address field is (addr >> 4): advancing by bytes/16 stays inside the 14-bit field
             const uint64_t ad = adesc0 + (uint64_t)(stage * (SLICE_BYTES_A >> 4));
             const uint64_t bd = bdesc0 + (uint64_t)(s * (SLICE_BYTES_W >> 4));
-            const uint64_t sd = sdesc0 + (uint64_t)(s * (SLICE_BYTES_S >> 4));
 #pragma unroll
             for (int kk = 0; kk < KSLICE / 16; ++kk) {
-              umma_f16_cg2(dmain, ad + 2 * kk, bd + 2 * kk, IDESC_MAIN, (s | kk) != 0);
-              umma_f16_cg2(dscore, ad + 2 * kk, sd + 2 * kk, IDESC_SCORE, (s | kk) != 0);
+              umma_f16_cg2(da, ad + 2 * kk, bd + 2 * kk, IDESC_A, (s | kk) != 0);
+              umma_f16_cg2(db, ad + 2 * kk, bd + ((W_ROWS_A * 128) >> 4) + 2 * kk, IDESC_B, (s | kk) != 0);
             }
             umma_commit_cg2_mc(bar_addr(sbase, B_EMPTY + stage), 3);
           }
@@ -240,7 +244,12 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         for (int sp = 0; sp < NSLICE; sp += 2) {
           // masks of two K-slices x two chunks: four independent Philox chains per thread (ILP),
           // drawn before the ring slot is known to be free
-          uint4 rnd[2][2];
+          uint4 rnd[2][2], hv[2][2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)     // the resident feature tile does not depend on the ring slot
+              hv[j][i] = *reinterpret_cast<const uint4*>(smem + SM_H + (sp + j) * SLICE_BYTES_A + off[i]);
           if constexpr (!INJECT) {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
@@ -261,7 +270,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
             mbar_wait(bar_addr(sbase, B_EMPTY + stage), phase ^ 1);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              const uint4 h = *reinterpret_cast<const uint4*>(smem + SM_H + s * SLICE_BYTES_A + off[i]);
+              const uint4 h = hv[j][i];
               uint4 o;
               if constexpr (!INJECT) {
                 o.x = h.x & keep_mask2(rnd[j][i].x, thr2);
@@ -315,10 +324,10 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         float acc[MAXC] = {0.f, 0.f, 0.f, 0.f};
         float* dbg_row = (P.dbg != nullptr && tc == 0)
                              ? P.dbg + ((size_t)(pair * 2 + (int)rank) * 128 + warp * 32 + lane) * 136 : nullptr;
-        if (half == 0) epilogue_half<0, NOUT>(P, lane_base + TM_MAIN + buf * 128, acc, dbg_row);
-        else           epilogue_half<1, NOUT>(P, lane_base + TM_MAIN + buf * 128, acc, dbg_row);
+        if (half == 0) epilogue_half<0, NOUT>(P, lane_base + buf * TM_BUF_STRIDE, acc, dbg_row);
+        else           epilogue_half<1, NOUT>(P, lane_base + buf * TM_BUF_STRIDE, acc, dbg_row);
         uint32_t sc[8];
-        tmem_ld8(lane_base + TM_SCORE + buf * 32, sc);
+        tmem_ld8(lane_base + buf * TM_BUF_STRIDE + TM_A + 64, sc);
         tmem_ld_wait();
         if (dbg_row) {
 #pragma unroll
@@ -395,7 +404,6 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
     ProjParams P;
     P.h16 = h16;
     P.wmain = w.d_wmain + (size_t)s * 2 * NSLICE * SLICE_BYTES_W;
-    P.wscore = w.d_wscore + (size_t)s * 2 * NSLICE * SLICE_BYTES_S;
     P.tiles = p.d_tiles;
     P.logits = logits; P.scores = scores;
     P.inj_feat = m.inj_feat; P.inj_attn = m.inj_attn;
