@@ -34,7 +34,7 @@ constexpr uint32_t SM_TOTAL = SM_BAR + 256;                        // 231680 <= 
 
 // barrier slots (8 bytes each) inside SM_BAR
 enum : uint32_t {
-  B_FULL = 0,                  // [3] leader only: masked A slice of both CTAs is in smem      (count 16)
+  B_FULL = 0,                  // [3] leader only: masked A slice of both CTAs is in smem      (count 8)
   B_EMPTY = B_FULL + 3,        // [3] per CTA: MMAs reading the stage have retired            (count 1)
   B_TFULL = B_EMPTY + 3,       // [2] per CTA: accumulator buffer complete                    (count 1)
   B_TEMPTY = B_TFULL + 2,      // [2] leader only: both CTAs' epilogues drained the buffer    (count 8)
@@ -131,7 +131,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 
   if ((sbase & 1023u) != 0) __trap();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(bar_addr(sbase, B_FULL + s), 2 * NUM_PRODUCER_WARPS); mbar_init(bar_addr(sbase, B_EMPTY + s), 1); }
+    for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(bar_addr(sbase, B_FULL + s), NUM_PRODUCER_WARPS /* 4 warps of one team x 2 CTAs */); mbar_init(bar_addr(sbase, B_EMPTY + s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_addr(sbase, B_TFULL + b), 1); mbar_init(bar_addr(sbase, B_TEMPTY + b), 8); }
     mbar_init(bar_addr(sbase, B_WLOC), 1);
     mbar_init(bar_addr(sbase, B_WREADY), 2);
@@ -214,17 +214,22 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     }
   } else if (warp >= PRODUCER_WARP0) {
     // ------------------------------------------------------------ producers: masked A slices
+    // Two teams of four warps: team 0 fills the even K-slices, team 1 the odd ones (16 rows x 8
+    // chunks per warp and slice = 4 chunks per thread).  The two producer warps that share an
+    // SM sub-partition belong to different teams, wait on different ring slots and therefore run
+    // out of phase: one is in its multiply-heavy Philox phase while the other masks / stores.
     const int pw = warp - PRODUCER_WARP0;
+    const int team = pw >> 2, wt = pw & 3;
     const uint32_t full_leader = mapa(bar_addr(sbase, B_FULL), 0);
     const uint32_t thr2 = P.thr_f | (P.thr_f << 16);
     const int chunk = lane & 7;
-    int rowi[2]; uint32_t off[2];
+    int rowi[4]; uint32_t off[4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      rowi[i] = pw * 8 + i * 4 + (lane >> 3);
+    for (int i = 0; i < 4; ++i) {
+      rowi[i] = wt * 16 + i * 4 + (lane >> 3);
       off[i] = (uint32_t)rowi[i] * 128u + (uint32_t)((chunk ^ (rowi[i] & 7)) << 4);
     }
-    uint32_t stage = 0, phase = 0;      // ring position of the next slice this warp fills
+    uint32_t stage = (uint32_t)team, phase = 0;      // ring position of this team's next slice
     int it = 0;
     for (long long u = u_begin; u < u_end; ++it) {
       const int ti = (int)(u / P.T);
@@ -234,66 +239,57 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       const TileDesc td = P.tiles[ti];
       mbar_wait(bar_addr(sbase, B_HFULL), (uint32_t)(it & 1));
       const uint32_t bag = (uint32_t)(P.bag_offset + td.gbag);
-      uint32_t nrow[2];
+      uint32_t nrow[4];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) nrow[i] = (uint32_t)(td.n0 + (int)rank * HALF_ROWS + rowi[i]);
+      for (int i = 0; i < 4; ++i) nrow[i] = (uint32_t)(td.n0 + (int)rank * HALF_ROWS + rowi[i]);
 #pragma unroll 1
       for (int t = t_begin; t < t_end; ++t) {
         const uint32_t tg = (uint32_t)(P.t_offset + t);
 #pragma unroll 1
-        for (int sp = 0; sp < NSLICE; sp += 2) {
-          // masks of two K-slices x two chunks: four independent Philox chains per thread (ILP),
-          // drawn before the ring slot is known to be free
-          uint4 rnd[2][2], hv[2][2];
+        for (int s = team; s < NSLICE; s += 2) {
+          // four independent Philox chains per thread, drawn (and the resident feature chunks
+          // loaded) before the ring slot is known to be free
+          uint4 rnd[4], hv[4];
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int i = 0; i < 2; ++i)     // the resident feature tile does not depend on the ring slot
-              hv[j][i] = *reinterpret_cast<const uint4*>(smem + SM_H + (sp + j) * SLICE_BYTES_A + off[i]);
+          for (int i = 0; i < 4; ++i)
+            hv[i] = *reinterpret_cast<const uint4*>(smem + SM_H + s * SLICE_BYTES_A + off[i]);
           if constexpr (!INJECT) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int i = 0; i < 4; ++i)
+              rnd[i] = philox4x32((uint32_t)(s * 8 + chunk), nrow[i], tg, bag, P.key);
+            // keep the chains ahead of the (volatile) barrier poll below: ptxas otherwise sinks the
+            // arithmetic behind the wait and serialises RNG latency with the ring hand-shake
 #pragma unroll
-              for (int i = 0; i < 2; ++i)
-                rnd[j][i] = philox4x32((uint32_t)((sp + j) * 8 + chunk), nrow[i], tg, bag, P.key);
-            // keep the four chains ahead of the (volatile) barrier polls below: ptxas otherwise sinks
-            // the arithmetic behind the wait and serialises RNG latency with the ring hand-shake
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-              for (int i = 0; i < 2; ++i)
-                asm volatile("" : "+r"(rnd[j][i].x), "+r"(rnd[j][i].y), "+r"(rnd[j][i].z), "+r"(rnd[j][i].w));
+            for (int i = 0; i < 4; ++i)
+              asm volatile("" : "+r"(rnd[i].x), "+r"(rnd[i].y), "+r"(rnd[i].z), "+r"(rnd[i].w));
           }
+          mbar_wait(bar_addr(sbase, B_EMPTY + stage), phase ^ 1);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int s = sp + j;
-            mbar_wait(bar_addr(sbase, B_EMPTY + stage), phase ^ 1);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const uint4 h = hv[j][i];
-              uint4 o;
-              if constexpr (!INJECT) {
-                o.x = h.x & keep_mask2(rnd[j][i].x, thr2);
-                o.y = h.y & keep_mask2(rnd[j][i].y, thr2);
-                o.z = h.z & keep_mask2(rnd[j][i].z, thr2);
-                o.w = h.w & keep_mask2(rnd[j][i].w, thr2);
-              } else {
-                const int trow = (int)rank * HALF_ROWS + rowi[i];
-                uint32_t bits = 0;
-                if (trow < td.nrows)
-                  bits = reinterpret_cast<const uint8_t*>(P.inj_feat)[((size_t)t * P.R + td.row0 + trow) * 64 + s * 8 + chunk];
-                o.x = h.x & ((bits & 1u ? 0x0000FFFFu : 0u) | (bits & 2u ? 0xFFFF0000u : 0u));
-                o.y = h.y & ((bits & 4u ? 0x0000FFFFu : 0u) | (bits & 8u ? 0xFFFF0000u : 0u));
-                o.z = h.z & ((bits & 16u ? 0x0000FFFFu : 0u) | (bits & 32u ? 0xFFFF0000u : 0u));
-                o.w = h.w & ((bits & 64u ? 0x0000FFFFu : 0u) | (bits & 128u ? 0xFFFF0000u : 0u));
-              }
-              *reinterpret_cast<uint4*>(smem + SM_RING + stage * SLICE_BYTES_A + off[i]) = o;
+          for (int i = 0; i < 4; ++i) {
+            const uint4 h = hv[i];
+            uint4 o;
+            if constexpr (!INJECT) {
+              o.x = h.x & keep_mask2(rnd[i].x, thr2);
+              o.y = h.y & keep_mask2(rnd[i].y, thr2);
+              o.z = h.z & keep_mask2(rnd[i].z, thr2);
+              o.w = h.w & keep_mask2(rnd[i].w, thr2);
+            } else {
+              const int trow = (int)rank * HALF_ROWS + rowi[i];
+              uint32_t bits = 0;
+              if (trow < td.nrows)
+                bits = reinterpret_cast<const uint8_t*>(P.inj_feat)[((size_t)t * P.R + td.row0 + trow) * 64 + s * 8 + chunk];
+              o.x = h.x & ((bits & 1u ? 0x0000FFFFu : 0u) | (bits & 2u ? 0xFFFF0000u : 0u));
+              o.y = h.y & ((bits & 4u ? 0x0000FFFFu : 0u) | (bits & 8u ? 0xFFFF0000u : 0u));
+              o.z = h.z & ((bits & 16u ? 0x0000FFFFu : 0u) | (bits & 32u ? 0xFFFF0000u : 0u));
+              o.w = h.w & ((bits & 64u ? 0x0000FFFFu : 0u) | (bits & 128u ? 0xFFFF0000u : 0u));
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(full_leader + stage * 8);
-            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+            *reinterpret_cast<uint4*>(smem + SM_RING + stage * SLICE_BYTES_A + off[i]) = o;
           }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(full_leader + stage * 8);
+          stage += 2;
+          if (stage >= NUM_STAGES) { stage -= NUM_STAGES; phase ^= 1; }
         }
       }
       __syncwarp();
