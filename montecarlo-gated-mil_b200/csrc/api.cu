@@ -132,7 +132,6 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu, const int32_t* bag_
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // host staging buffers go out of scope
   if (e != cudaSuccess) { mcmil_plan_destroy(p); return cuda_fail(e, "mcmil_plan_create"); }
   size_t off = 0;
-  p->off_h16 = off;     off = align_up(off + (size_t)p->n_tiles * TILE_H16_BYTES, 1024);
   p->off_logit = off;   off = align_up(off + (size_t)T * p->C * p->Rp * sizeof(float), 1024);
   p->off_score = off;   off = align_up(off + (size_t)T * p->C * p->Rp * sizeof(float), 1024);
   p->off_rowstat = off; off = align_up(off + (size_t)T * p->C * n_bags * sizeof(float2), 1024);
@@ -170,19 +169,15 @@ int mcmil_head_forward(const mcmil_weights_t* w, const mcmil_plan_t* plan, const
     return fail(MCMIL_E_UNSUPPORTED, "mcmil_head_forward: tcgen05 path supports p_f <= 0.96 or p_f == 1");
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  uint8_t* h16 = ws + plan->off_h16;
   float* logits = reinterpret_cast<float*>(ws + plan->off_logit);
   float* scores = reinterpret_cast<float*>(ws + plan->off_score);
   float2* rowstat = reinterpret_cast<float2*>(ws + plan->off_rowstat);
   const MaskSpec m = make_mask_spec(t_offset, bag_offset, seed, p_f, p_a, inj_feat, inj_attn);
   cudaError_t e;
   if (impl == MCMIL_IMPL_TCGEN05) {
-    e = launch_pack_h16(*plan, H, h16, st, &g_launches);
-    if (e != cudaSuccess) return cuda_fail(e, "pack_h16");
-    // MCMIL_DEBUG_DUMP: prob_m2 doubles as nothing — debug dumps go through mcmil_debug_forward
     const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
     if (prof) cudaEventRecord(g_prof.ev[g_prof.used], st);
-    e = launch_proj_tc(*w, *plan, m, h16, logits, scores, nullptr, st, &g_launches);
+    e = launch_proj_tc(*w, *plan, m, H, logits, scores, nullptr, st, &g_launches);
     if (prof) { cudaEventRecord(g_prof.ev[g_prof.used + 1], st); g_prof.used += 2; g_prof.kernels += w->S; }
     if (e != cudaSuccess) return cuda_fail(e, "proj_tc");
   } else if (impl == MCMIL_IMPL_SIMT_FP32) {
@@ -210,8 +205,7 @@ int mcmil_debug_proj_tc(const mcmil_weights_t* w, const mcmil_plan_t* plan, cons
   float* scores = reinterpret_cast<float*>(ws + plan->off_score);
   const MaskSpec m = make_mask_spec(t_offset, bag_offset, seed, p_f, p_a, inj_feat, inj_attn);
   int launches = 0;
-  cudaError_t e = launch_pack_h16(*plan, H, ws + plan->off_h16, st, &launches);
-  if (e == cudaSuccess) e = launch_proj_tc(*w, *plan, m, ws + plan->off_h16, logits, scores, dbg, st, &launches);
+  cudaError_t e = launch_proj_tc(*w, *plan, m, H, logits, scores, dbg, st, &launches);
   const size_t plane = (size_t)plan->T * plan->C * plan->Rp * sizeof(float);
   if (e == cudaSuccess && logits_out) e = cudaMemcpyAsync(logits_out, logits, plane, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess && scores_out) e = cudaMemcpyAsync(scores_out, scores, plane, cudaMemcpyDeviceToDevice, st);

@@ -22,7 +22,6 @@ constexpr int SLICE_BYTES_A = HALF_ROWS * 128;   // 8 KB : 64 rows x 128 B
 // ~48 tensor-pipe cycles per K=16 step instead of the 4 the math needs: profiles/r1.)
 constexpr int W_ROWS_A = 72, W_ROWS_B = 64, W_ROWS = W_ROWS_A + W_ROWS_B;
 constexpr int SLICE_BYTES_W = W_ROWS * 128;      // 17 KB
-constexpr int TILE_H16_BYTES = 2 * NSLICE * SLICE_BYTES_A;  // 128 KB per pair tile
 
 // One pair tile = up to 128 consecutive patches of one bag.
 struct TileDesc {

@@ -35,7 +35,7 @@ struct Plan {
   int32_t* d_row2bag = nullptr;  // [R]
   int32_t* d_gbag = nullptr;     // [n_bags] global bag ids
   // workspace layout (byte offsets)
-  size_t off_h16 = 0, off_logit = 0, off_score = 0, off_rowstat = 0, ws_bytes = 0;
+  size_t off_logit = 0, off_score = 0, off_rowstat = 0, ws_bytes = 0;
 };
 
 struct MaskSpec {
@@ -51,8 +51,7 @@ struct MaskSpec {
 cudaError_t launch_pack_weights(Weights& w, const float* attV_w, const float* attV_b, const float* attU_w,
                                 const float* attU_b, const float* attw_w, const float* attw_b,
                                 const float* cls_w, cudaStream_t st);
-cudaError_t launch_pack_h16(const Plan& p, const float* H, uint8_t* h16, cudaStream_t st, int* launches);
-cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const uint8_t* h16,
+cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const float* H,
                            float* logits, float* scores, float* dbg, cudaStream_t st, int* launches);
 cudaError_t launch_proj_simt(const Weights& w, const Plan& p, const MaskSpec& m, const float* H,
                              float* logits, float* scores, cudaStream_t st, int* launches);

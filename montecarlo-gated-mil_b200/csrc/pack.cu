@@ -1,8 +1,7 @@
-// pack.cu — layout kernels: weights -> UMMA shared-memory images, features -> fp16 K-major
-// swizzled tiles, and the Philox keep-bit export used by the tests.
+// pack.cu — layout kernels: weights -> UMMA shared-memory images (fp16, K-major, 128-byte
+// swizzle) and the Philox keep-bit export used by the tests.
 //
-// Parameters packed here are the ones model.py:181-203 defines; the feature tile is the
-// H of model.py:276-277 (one bag's (N,512) ResNet features).
+// Parameters packed here are the ones model.py:181-203 defines.
 #include "internal.h"
 
 namespace mcmil {
@@ -95,40 +94,6 @@ cudaError_t launch_pack_weights(Weights& w, const float* attV_w, const float* at
     }
   }
   return cudaSuccess;
-}
-
-// ------------------------------------------------------------------ features -> fp16 tiles
-// h16: [n_tiles][2 ranks][8 slices][64 rows][128 B] swizzled; rows beyond the bag are zero.
-__global__ void pack_h16_kernel(const float* __restrict__ H, const TileDesc* __restrict__ tiles,
-                                uint8_t* __restrict__ h16) {
-  const int half = blockIdx.x;            // tile*2 + rank
-  const TileDesc td = tiles[half >> 1];
-  const int rank = half & 1;
-  uint8_t* dst = h16 + (size_t)half * (NSLICE * SLICE_BYTES_A);
-  for (int i = threadIdx.x; i < HALF_ROWS * (L / 8); i += blockDim.x) {
-    const int q = i & 63;                 // 8-feature chunk within the row
-    const int rr = i >> 6;                // row within the half tile
-    const int trow = rank * HALF_ROWS + rr;
-    uint4 packed = make_uint4(0, 0, 0, 0);
-    if (trow < td.nrows) {
-      const float4* src = reinterpret_cast<const float4*>(H + (size_t)(td.row0 + trow) * L + q * 8);
-      const float4 a = __ldg(src), b = __ldg(src + 1);
-      const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
-      const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
-      packed.x = *reinterpret_cast<const uint32_t*>(&h0);
-      packed.y = *reinterpret_cast<const uint32_t*>(&h1);
-      packed.z = *reinterpret_cast<const uint32_t*>(&h2);
-      packed.w = *reinterpret_cast<const uint32_t*>(&h3);
-    }
-    const int slice = q >> 3, c = q & 7;
-    *reinterpret_cast<uint4*>(dst + slice * SLICE_BYTES_A + rr * 128 + ((c ^ (rr & 7)) << 4)) = packed;
-  }
-}
-
-cudaError_t launch_pack_h16(const Plan& p, const float* H, uint8_t* h16, cudaStream_t st, int* launches) {
-  pack_h16_kernel<<<p.n_tiles * 2, 256, 0, st>>>(H, p.d_tiles, h16);
-  if (launches) ++*launches;
-  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ mask export (tests)

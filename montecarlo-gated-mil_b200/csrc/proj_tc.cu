@@ -6,15 +6,17 @@
 //     logit[t,c,n] = ( sum_d tanh(Hd Wv^T + bv)_d * sigmoid(Hd Wu^T + bu)_d * w_c[d] + b_c ) * keep_a / (1-p_a)
 //     score[t,c,n] = Hd[t,n,:] . wc_c / (1-p_f)
 //
-// One persistent 2-CTA cluster per SM pair; the pair shares one tcgen05.mma.cta_group::2 of
-// M=128 (64 patches per CTA) x N=256 (V|U columns, half resident in each CTA's smem) x K=512.
-// Everything that is re-used across the T samples stays on chip:
-//   smem  : W (fp16, 128 KB/CTA, loaded once per kernel by TMA bulk copies), the fp16 feature
-//           tile (64 KB/CTA, one TMA load per work item), a 3-stage ring of masked A slices;
-//   TMEM  : two 128x256 fp32 accumulators (double buffered across t) + score columns.
+// One persistent 2-CTA cluster per SM pair; the pair shares tcgen05.mma.cta_group::2 tiles of
+// M=128 (64 patches per CTA) x N=144+128 (tanh | sigmoid | score columns, half of the W rows
+// resident in each CTA's smem) x K=512.  Everything re-used across the T samples stays on chip:
+//   smem : W (fp16, 136 KB/CTA, loaded once per kernel by TMA bulk copies) and an 8-slot ring of
+//          masked fp16 A slices (slot = K-slice, 64 KB/CTA, a full sample deep);
+//   regs : each producer thread keeps ITS 16 chunks of the fp16 feature tile in registers for the
+//          whole work item (converted from the fp32 features once per item);
+//   TMEM : two accumulator buffers (double buffered across t).
 // Warp roles (14 warps): 0-3 epilogue (TMEM -> tanh/sigmoid/gate/w-dot -> logits),
 //   4-11 producers (Philox mask -> masked fp16 A slice, generic-proxy st.shared + proxy fence),
-//   12 MMA issuer (+TMEM alloc), 13 TMA loader.
+//   12, 13 MMA issuers (even / odd samples; 12 owns the TMEM allocation, 13 first TMA-loads W).
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -22,28 +24,27 @@ namespace mcmil {
 using namespace ptx;
 
 constexpr int TC_THREADS = 14 * 32;
-constexpr int NUM_STAGES = 3;
-constexpr int PRODUCER_WARP0 = 4, NUM_PRODUCER_WARPS = 8, MMA_WARP = 12, LOAD_WARP = 13;
+constexpr int PRODUCER_WARP0 = 4, MMA_WARP = 12, LOAD_WARP = 13;   // warps 4..11 produce
+constexpr int TEAM_WARPS = 4;                    // two teams of four producer warps
 
 constexpr uint32_t SM_W = 0;
-constexpr uint32_t SM_H = SM_W + NSLICE * SLICE_BYTES_W;           // 139264
-constexpr uint32_t SM_RING = SM_H + NSLICE * SLICE_BYTES_A;        // 204800
-constexpr uint32_t SM_XCH = SM_RING + NUM_STAGES * SLICE_BYTES_A;  // 229376  [2][64][4] floats
-constexpr uint32_t SM_BAR = SM_XCH + 2 * HALF_ROWS * MAXC * 4;     // 231424
-constexpr uint32_t SM_TOTAL = SM_BAR + 256;                        // 231680 <= 232448 (227 KB)
+constexpr uint32_t SM_RING = SM_W + NSLICE * SLICE_BYTES_W;        // 139264: 8 slots x 8 KB
+constexpr uint32_t SM_XCH = SM_RING + NSLICE * SLICE_BYTES_A;      // 204800: [2][64][4] floats
+constexpr uint32_t SM_BAR = SM_XCH + 2 * HALF_ROWS * MAXC * 4;     // 206848
+constexpr uint32_t SM_TOTAL = SM_BAR + 512;                        // 207360 <= 232448 (227 KB)
 
-// barrier slots (8 bytes each) inside SM_BAR
+// barrier slots (8 bytes each) inside SM_BAR.  The ring barriers exist twice, one set per sample
+// parity: samples are issued alternately by two MMA warps, and each warp must only ever see
+// consecutive phases of the barriers it waits on.
 enum : uint32_t {
-  B_FULL = 0,                  // [3] leader only: masked A slice of both CTAs is in smem      (count 8)
-  B_EMPTY = B_FULL + 3,        // [3] per CTA: MMAs reading the stage have retired            (count 1)
-  B_TFULL = B_EMPTY + 3,       // [2] per CTA: accumulator buffer complete                    (count 1)
-  B_TEMPTY = B_TFULL + 2,      // [2] leader only: both CTAs' epilogues drained the buffer    (count 8)
-  B_WLOC = B_TEMPTY + 2,       // per CTA: W bulk copies landed                               (tx)
-  B_WREADY = B_WLOC + 1,       // leader only: both CTAs hold their W halves                  (count 2)
-  B_HFULL = B_WREADY + 1,      // per CTA: feature tile landed                                (tx)
-  B_HEMPTY = B_HFULL + 1,      // per CTA: producers finished with the feature tile           (count 8)
-  B_COUNT = B_HEMPTY + 1,
-  TMEM_SLOT = 30               // uint32 at SM_BAR + 8*30
+  B_FULL = 0,                      // [2][8] leader only: masked A slice of both CTAs is in smem (count 2 x TEAM_WARPS)
+  B_EMPTY = B_FULL + 2 * NSLICE,   // [2][8] per CTA: the MMAs reading the slot have retired     (count 1)
+  B_TFULL = B_EMPTY + 2 * NSLICE,  // [2] per CTA: accumulator buffer complete                   (count 1)
+  B_TEMPTY = B_TFULL + 2,          // [2] leader only: both CTAs' epilogues drained the buffer   (count 8)
+  B_WLOC = B_TEMPTY + 2,           // per CTA: W bulk copies landed                              (tx)
+  B_WREADY = B_WLOC + 1,           // leader only: both CTAs hold their W halves                 (count 2)
+  B_COUNT = B_WREADY + 1,
+  TMEM_SLOT = 48                   // uint32 at SM_BAR + 8*48
 };
 
 // TMEM columns of one accumulator buffer (2x2 layout of the pair MMAs: lanes 0..63 hold the
@@ -54,7 +55,7 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_A = 0, TM_B = 96, TM_BUF_STRIDE = 160;
 
 struct ProjParams {
-  const uint8_t* h16;      // [n_tiles][2][8][8 KB]
+  const float* H;          // [R][512] fp32 packed features
   const uint8_t* wmain;    // this set: [2][8][17 KB]
   const TileDesc* tiles;
   float* logits;           // [T][C][Rp]
@@ -83,8 +84,12 @@ __device__ __forceinline__ uint32_t keep_mask2(uint32_t r, uint32_t thr2) {
   asm("set.geu.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(thr2));
   return m;
 }
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 
-template <int HALF, int NOUT>
+template <int HALF, int NOUT, bool DEBUG>
 __device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tbuf, float (&acc)[MAXC],
                                               float* dbg_row) {
 #pragma unroll
@@ -96,11 +101,13 @@ __device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tbuf
       tmem_ld16(tcol + 16 * j, v);
       tmem_ld16(tcol + 32 + 16 * j, u);
       tmem_ld_wait();
-      if (dbg_row) {
+      if constexpr (DEBUG) {
+        if (dbg_row) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          dbg_row[64 * part + 16 * j + i] = __uint_as_float(v[i]);
-          dbg_row[64 * part + 32 + 16 * j + i] = __uint_as_float(u[i]);
+          for (int i = 0; i < 16; ++i) {
+            dbg_row[64 * part + 16 * j + i] = __uint_as_float(v[i]);
+            dbg_row[64 * part + 32 + 16 * j + i] = __uint_as_float(u[i]);
+          }
         }
       }
 #pragma unroll
@@ -116,7 +123,7 @@ __device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tbuf
   }
 }
 
-template <int NOUT, bool INJECT>
+template <int NOUT, bool INJECT, bool DEBUG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 proj_tc_kernel(const __grid_constant__ ProjParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -131,12 +138,13 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 
   if ((sbase & 1023u) != 0) __trap();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(bar_addr(sbase, B_FULL + s), NUM_PRODUCER_WARPS /* 4 warps of one team x 2 CTAs */); mbar_init(bar_addr(sbase, B_EMPTY + s), 1); }
+    for (int s = 0; s < 2 * NSLICE; ++s) {
+      mbar_init(bar_addr(sbase, B_FULL + s), 2 * TEAM_WARPS);
+      mbar_init(bar_addr(sbase, B_EMPTY + s), 1);
+    }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_addr(sbase, B_TFULL + b), 1); mbar_init(bar_addr(sbase, B_TEMPTY + b), 8); }
     mbar_init(bar_addr(sbase, B_WLOC), 1);
     mbar_init(bar_addr(sbase, B_WREADY), 2);
-    mbar_init(bar_addr(sbase, B_HFULL), 1);
-    mbar_init(bar_addr(sbase, B_HEMPTY), NUM_PRODUCER_WARPS);
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
@@ -149,66 +157,55 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * TMEM_SLOT);
 
-  if (warp == LOAD_WARP) {
-    // ------------------------------------------------------------ TMA loader
-    if (lane == 0) {
+  if (warp == MMA_WARP || warp == LOAD_WARP) {
+    // ------------------------------------------------------------ TMA loader: this CTA's W rows, once
+    if (warp == LOAD_WARP && lane == 0) {
       const uint32_t wloc = bar_addr(sbase, B_WLOC);
       mbar_expect_tx(wloc, NSLICE * SLICE_BYTES_W);
       for (int s = 0; s < NSLICE; ++s)
         bulk_g2s(sbase + SM_W + s * SLICE_BYTES_W, P.wmain + (size_t)(rank * NSLICE + s) * SLICE_BYTES_W, SLICE_BYTES_W, wloc);
       mbar_wait(wloc, 0);
       mbar_arrive_cluster(mapa(bar_addr(sbase, B_WREADY), 0));
-      const uint32_t hfull = bar_addr(sbase, B_HFULL), hempty = bar_addr(sbase, B_HEMPTY);
-      int it = 0;
-      for (long long u = u_begin; u < u_end; ++it) {
-        const int ti = (int)(u / P.T);
-        const long long u_next = (long long)(ti + 1) * P.T;
-        if (it > 0) mbar_wait(hempty, (uint32_t)((it - 1) & 1));
-        mbar_expect_tx(hfull, NSLICE * SLICE_BYTES_A);
-        const uint8_t* src = P.h16 + ((size_t)ti * 2 + rank) * (NSLICE * SLICE_BYTES_A);
-        for (int s = 0; s < NSLICE; ++s)
-          bulk_g2s(sbase + SM_H + s * SLICE_BYTES_A, src + (size_t)s * SLICE_BYTES_A, SLICE_BYTES_A, hfull);
-        u = u_next < u_end ? u_next : u_end;
-      }
     }
-  } else if (warp == MMA_WARP) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA)
-    // The whole warp runs the loop so that every address / descriptor stays in uniform registers;
-    // one elected lane issues the tcgen05 instructions (a lane-0-only loop makes ptxas emit
-    // ELECT + R2UR chains per MMA and the issue thread becomes the bottleneck, profiles/r1).
+    __syncwarp();
+    // ------------------------------------------------------------ MMA issuers (leader CTA)
+    // Two issue warps, one per sample parity / accumulator buffer: a single warp shares its
+    // scheduler with three busy warps and needs ~500 cycles of issue latency per K-slice, twice the
+    // 272 cycles of tensor work it launches (profiles/r1).  Each warp runs its loop warp-uniformly
+    // (addresses / descriptors in uniform registers: a lane-0-only loop makes ptxas emit ELECT +
+    // R2UR chains per MMA); one elected lane issues the tcgen05 ops.
     if (rank == 0) {
       constexpr uint32_t IDESC_A = umma_idesc_f16(128, 2 * W_ROWS_A);
       constexpr uint32_t IDESC_B = umma_idesc_f16(128, 2 * W_ROWS_B);
+      const uint32_t q = (uint32_t)(warp - MMA_WARP);          // sample parity and TMEM buffer of this warp
       mbar_wait(bar_addr(sbase, B_WREADY), 0);
       tc_fence_after();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t adesc0 = umma_desc_sw128(sbase + SM_RING);
       const uint64_t bdesc0 = umma_desc_sw128(sbase + SM_W);
-      uint32_t stage = 0, phase = 0, tc = 0;
-      for (long long u = u_begin; u < u_end; ++u, ++tc) {
-        const uint32_t buf = tc & 1;
-        mbar_wait(bar_addr(sbase, B_TEMPTY + buf), ((tc >> 1) & 1) ^ 1);
+      const uint32_t da = tmem_u + q * TM_BUF_STRIDE + TM_A, db = tmem_u + q * TM_BUF_STRIDE + TM_B;
+      uint32_t j = 0;                                           // this warp's sample counter
+      for (long long u = u_begin + q; u < u_end; u += 2, ++j) {
+        mbar_wait(bar_addr(sbase, B_TEMPTY + q), (j & 1) ^ 1);
         tc_fence_after();
-        const uint32_t da = tmem_u + buf * TM_BUF_STRIDE + TM_A, db = tmem_u + buf * TM_BUF_STRIDE + TM_B;
 #pragma unroll 1
         for (int s = 0; s < NSLICE; ++s) {
-          mbar_wait(bar_addr(sbase, B_FULL + stage), phase);
+          mbar_wait(bar_addr(sbase, B_FULL + q * NSLICE + s), j & 1);
           tc_fence_after();
           if (elect_one()) {
             // start-address field is (addr >> 4): advancing by bytes/16 stays inside the 14-bit field
-            const uint64_t ad = adesc0 + (uint64_t)(stage * (SLICE_BYTES_A >> 4));
+            const uint64_t ad = adesc0 + (uint64_t)(s * (SLICE_BYTES_A >> 4));
             const uint64_t bd = bdesc0 + (uint64_t)(s * (SLICE_BYTES_W >> 4));
 #pragma unroll
             for (int kk = 0; kk < KSLICE / 16; ++kk) {
               umma_f16_cg2(da, ad + 2 * kk, bd + 2 * kk, IDESC_A, (s | kk) != 0);
               umma_f16_cg2(db, ad + 2 * kk, bd + ((W_ROWS_A * 128) >> 4) + 2 * kk, IDESC_B, (s | kk) != 0);
             }
-            umma_commit_cg2_mc(bar_addr(sbase, B_EMPTY + stage), 3);
+            umma_commit_cg2_mc(bar_addr(sbase, B_EMPTY + q * NSLICE + s), 3);
           }
           __syncwarp();
-          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) umma_commit_cg2_mc(bar_addr(sbase, B_TFULL + buf), 3);
+        if (elect_one()) umma_commit_cg2_mc(bar_addr(sbase, B_TFULL + q), 3);
         __syncwarp();
       }
     }
@@ -216,8 +213,8 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     // ------------------------------------------------------------ producers: masked A slices
     // Two teams of four warps: team 0 fills the even K-slices, team 1 the odd ones (16 rows x 8
     // chunks per warp and slice = 4 chunks per thread).  The two producer warps that share an
-    // SM sub-partition belong to different teams, wait on different ring slots and therefore run
-    // out of phase: one is in its multiply-heavy Philox phase while the other masks / stores.
+    // SM sub-partition belong to different teams.  The ring is a full sample deep (slot = K-slice),
+    // so a warp only ever waits for the MMAs of the PREVIOUS sample.
     const int pw = warp - PRODUCER_WARP0;
     const int team = pw >> 2, wt = pw & 3;
     const uint32_t full_leader = mapa(bar_addr(sbase, B_FULL), 0);
@@ -229,44 +226,56 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       rowi[i] = wt * 16 + i * 4 + (lane >> 3);
       off[i] = (uint32_t)rowi[i] * 128u + (uint32_t)((chunk ^ (rowi[i] & 7)) << 4);
     }
-    uint32_t stage = (uint32_t)team, phase = 0;      // ring position of this team's next slice
-    int it = 0;
-    for (long long u = u_begin; u < u_end; ++it) {
+    uint32_t tc = 0;                                  // samples processed so far by this pair
+    for (long long u = u_begin; u < u_end;) {
       const int ti = (int)(u / P.T);
       const int t_begin = (int)(u - (long long)ti * P.T);
       const long long u_next = (long long)(ti + 1) * P.T;
       const int t_end = (int)((u_next < u_end ? u_next : u_end) - (long long)ti * P.T);
       const TileDesc td = P.tiles[ti];
-      mbar_wait(bar_addr(sbase, B_HFULL), (uint32_t)(it & 1));
       const uint32_t bag = (uint32_t)(P.bag_offset + td.gbag);
+      // this thread's 16 chunks (4 slices of its team x 4 row slots) of the fp16 feature tile: registers
+      uint4 hreg[4][4];
       uint32_t nrow[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) nrow[i] = (uint32_t)(td.n0 + (int)rank * HALF_ROWS + rowi[i]);
-#pragma unroll 1
-      for (int t = t_begin; t < t_end; ++t) {
-        const uint32_t tg = (uint32_t)(P.t_offset + t);
-#pragma unroll 1
-        for (int s = team; s < NSLICE; s += 2) {
-          // four independent Philox chains per thread, drawn (and the resident feature chunks
-          // loaded) before the ring slot is known to be free
-          uint4 rnd[4], hv[4];
+      for (int i = 0; i < 4; ++i) {
+        const int trow = (int)rank * HALF_ROWS + rowi[i];
+        nrow[i] = (uint32_t)(td.n0 + trow);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            hv[i] = *reinterpret_cast<const uint4*>(smem + SM_H + s * SLICE_BYTES_A + off[i]);
-          if constexpr (!INJECT) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              rnd[i] = philox4x32((uint32_t)(s * 8 + chunk), nrow[i], tg, bag, P.key);
-            // keep the chains ahead of the (volatile) barrier poll below: ptxas otherwise sinks the
-            // arithmetic behind the wait and serialises RNG latency with the ring hand-shake
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              asm volatile("" : "+r"(rnd[i].x), "+r"(rnd[i].y), "+r"(rnd[i].z), "+r"(rnd[i].w));
+        for (int si = 0; si < 4; ++si) {
+          uint4 packed = make_uint4(0, 0, 0, 0);
+          if (trow < td.nrows) {
+            const float4* src = reinterpret_cast<const float4*>(
+                P.H + (size_t)(td.row0 + trow) * L + (2 * si + team) * KSLICE + chunk * 8);
+            const float4 a = __ldg(src), b = __ldg(src + 1);
+            packed.x = pack_half2(a.x, a.y); packed.y = pack_half2(a.z, a.w);
+            packed.z = pack_half2(b.x, b.y); packed.w = pack_half2(b.z, b.w);
           }
-          mbar_wait(bar_addr(sbase, B_EMPTY + stage), phase ^ 1);
+          hreg[si][i] = packed;
+        }
+      }
+      // Software pipeline: the Philox words of the NEXT slice are drawn next to the masking /
+      // st.shared of the CURRENT one, so wide multiplies (fmaheavy pipe) and ALU / LSU work mix.
+      uint4 rnd[4];
+      if constexpr (!INJECT) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          rnd[i] = philox4x32((uint32_t)(team * 8 + chunk), nrow[i], (uint32_t)(P.t_offset + t_begin), bag, P.key);
+      }
+#pragma unroll 1
+      for (int t = t_begin; t < t_end; ++t, ++tc) {
+        const uint32_t tg = (uint32_t)(P.t_offset + t);
+        // slot s was last read by the MMAs of sample tc-1, issued by warp (tc-1)&1 as its ((tc-1)>>1)-th
+        const uint32_t empty_set = ((tc + 1) & 1) * NSLICE, empty_parity = ((tc - 1) >> 1) & 1;
+        const uint32_t full_set = (tc & 1) * NSLICE;
+#pragma unroll
+        for (int si = 0; si < 4; ++si) {
+          const int s = 2 * si + team;
+          if (tc > 0) mbar_wait(bar_addr(sbase, B_EMPTY + empty_set + s), empty_parity);
+          uint4 nxt[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint4 h = hv[i];
+            const uint4 h = hreg[si][i];
             uint4 o;
             if constexpr (!INJECT) {
               o.x = h.x & keep_mask2(rnd[i].x, thr2);
@@ -283,22 +292,29 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
               o.z = h.z & ((bits & 16u ? 0x0000FFFFu : 0u) | (bits & 32u ? 0xFFFF0000u : 0u));
               o.w = h.w & ((bits & 64u ? 0x0000FFFFu : 0u) | (bits & 128u ? 0xFFFF0000u : 0u));
             }
-            *reinterpret_cast<uint4*>(smem + SM_RING + stage * SLICE_BYTES_A + off[i]) = o;
+            *reinterpret_cast<uint4*>(smem + SM_RING + s * SLICE_BYTES_A + off[i]) = o;
+          }
+          if constexpr (!INJECT) {
+            // next slice of this team: (s + 2, t), or (team, t + 1) after the last one of the sample
+            const uint32_t q_next = (uint32_t)((si < 3 ? s + 2 : team) * 8 + chunk);
+            const uint32_t t_next = si < 3 ? tg : tg + 1u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) nxt[i] = philox4x32(q_next, nrow[i], t_next, bag, P.key);
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(full_leader + stage * 8);
-          stage += 2;
-          if (stage >= NUM_STAGES) { stage -= NUM_STAGES; phase ^= 1; }
+          if (lane == 0) mbar_arrive_cluster(full_leader + (full_set + s) * 8);
+          if constexpr (!INJECT) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rnd[i] = nxt[i];
+          }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_addr(sbase, B_HEMPTY));
       u = u_next < u_end ? u_next : u_end;
     }
   } else {
     // ------------------------------------------------------------ epilogue warps 0..3
-    const int half = warp >> 1;                    // TMEM lanes 64..127 hold hidden units 64..127
+    const int half = warp >> 1;                    // TMEM lanes 64..127: the peer CTA's W rows
     const int r = (warp & 1) * 32 + lane;          // patch row within this CTA's 64-row half tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t tempty_leader = mapa(bar_addr(sbase, B_TEMPTY), 0);
@@ -318,16 +334,21 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         mbar_wait(bar_addr(sbase, B_TFULL + buf), (tc >> 1) & 1);
         tc_fence_after();
         float acc[MAXC] = {0.f, 0.f, 0.f, 0.f};
-        float* dbg_row = (P.dbg != nullptr && tc == 0)
-                             ? P.dbg + ((size_t)(pair * 2 + (int)rank) * 128 + warp * 32 + lane) * 136 : nullptr;
-        if (half == 0) epilogue_half<0, NOUT>(P, lane_base + buf * TM_BUF_STRIDE, acc, dbg_row);
-        else           epilogue_half<1, NOUT>(P, lane_base + buf * TM_BUF_STRIDE, acc, dbg_row);
+        float* dbg_row = nullptr;
+        if constexpr (DEBUG) {
+          if (P.dbg != nullptr && tc == 0)
+            dbg_row = P.dbg + ((size_t)(pair * 2 + (int)rank) * 128 + warp * 32 + lane) * 136;
+        }
+        if (half == 0) epilogue_half<0, NOUT, DEBUG>(P, lane_base + buf * TM_BUF_STRIDE, acc, dbg_row);
+        else           epilogue_half<1, NOUT, DEBUG>(P, lane_base + buf * TM_BUF_STRIDE, acc, dbg_row);
         uint32_t sc[8];
         tmem_ld8(lane_base + buf * TM_BUF_STRIDE + TM_A + 64, sc);
         tmem_ld_wait();
-        if (dbg_row) {
+        if constexpr (DEBUG) {
+          if (dbg_row) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dbg_row[128 + i] = __uint_as_float(sc[i]);
+            for (int i = 0; i < 8; ++i) dbg_row[128 + i] = __uint_as_float(sc[i]);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -346,17 +367,15 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
             rnd = attn_words(0u, (uint32_t)(td.n0 + trow), tg, (uint32_t)(P.bag_offset + td.gbag), P.key);
 #pragma unroll
           for (int c = 0; c < NOUT; ++c) {
-            {
-              const int head = P.head0 + c;
-              float logit = acc[c] + x[c] + P.epi.bw[c];
-              bool keep;
-              if constexpr (!INJECT) keep = attn_keep_from(rnd, head, P.thr_a);
-              else keep = (P.inj_attn[((size_t)t * P.C + head) * (P.Rp >> 5) + (g >> 5)] >> (g & 31)) & 1u;
-              logit = keep ? logit * P.sa : 0.f;           // a dropped logit is 0, not -inf (model.py:291,305)
-              const size_t o = ((size_t)t * P.C + head) * P.Rp + g;
-              P.logits[o] = logit;
-              P.scores[o] = (__uint_as_float(sc[c]) + __uint_as_float(sc[4 + c])) * P.sf;
-            }
+            const int head = P.head0 + c;
+            float logit = acc[c] + x[c] + P.epi.bw[c];
+            bool keep;
+            if constexpr (!INJECT) keep = attn_keep_from(rnd, head, P.thr_a);
+            else keep = (P.inj_attn[((size_t)t * P.C + head) * (P.Rp >> 5) + (g >> 5)] >> (g & 31)) & 1u;
+            logit = keep ? logit * P.sa : 0.f;           // a dropped logit is 0, not -inf (model.py:291,305)
+            const size_t o = ((size_t)t * P.C + head) * P.Rp + g;
+            P.logits[o] = logit;
+            P.scores[o] = (__uint_as_float(sc[c]) + __uint_as_float(sc[4 + c])) * P.sf;
           }
         }
       }
@@ -374,12 +393,15 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
   }
 }
 
-cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const uint8_t* h16,
+cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const float* H,
                            float* logits, float* scores, float* dbg, cudaStream_t st, int* launches) {
   using KernelFn = void (*)(ProjParams);
   static const KernelFn kernels[2][4] = {
-      {proj_tc_kernel<1, false>, proj_tc_kernel<2, false>, proj_tc_kernel<3, false>, proj_tc_kernel<4, false>},
-      {proj_tc_kernel<1, true>, proj_tc_kernel<2, true>, proj_tc_kernel<3, true>, proj_tc_kernel<4, true>}};
+      {proj_tc_kernel<1, false, false>, proj_tc_kernel<2, false, false>, proj_tc_kernel<3, false, false>,
+       proj_tc_kernel<4, false, false>},
+      {proj_tc_kernel<1, true, false>, proj_tc_kernel<2, true, false>, proj_tc_kernel<3, true, false>,
+       proj_tc_kernel<4, true, false>}};
+  static const KernelFn debug_kernel = proj_tc_kernel<2, false, true>;   // raw-accumulator dump (tests only)
   static bool attr_set = false;
   if (!attr_set) {
     for (int a = 0; a < 2; ++a)
@@ -387,8 +409,11 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
         cudaError_t e = cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
         if (e != cudaSuccess) return e;
       }
+    cudaError_t e = cudaFuncSetAttribute(debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+    if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  if (dbg != nullptr && !(w.shared && w.C == 2 && m.inj_feat == nullptr)) return cudaErrorInvalidValue;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -398,7 +423,7 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
   if (n_pairs < 1) return cudaSuccess;
   for (int s = 0; s < w.S; ++s) {
     ProjParams P;
-    P.h16 = h16;
+    P.H = H;
     P.wmain = w.d_wmain + (size_t)s * 2 * NSLICE * SLICE_BYTES_W;
     P.tiles = p.d_tiles;
     P.logits = logits; P.scores = scores;
@@ -412,7 +437,8 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
     P.sf = m.sf; P.hsf = 0.5f * m.sf; P.sa = m.sa;
     P.key = m.key;
     P.epi = w.epi[s];
-    kernels[m.inj_feat != nullptr ? 1 : 0][P.n_out - 1]<<<2 * n_pairs, TC_THREADS, SM_TOTAL, st>>>(P);
+    const KernelFn fn = dbg != nullptr ? debug_kernel : kernels[m.inj_feat != nullptr ? 1 : 0][P.n_out - 1];
+    fn<<<2 * n_pairs, TC_THREADS, SM_TOTAL, st>>>(P);
     if (launches) ++*launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
