@@ -63,9 +63,14 @@ softmax_rows_kernel(const float* __restrict__ logits, const float* __restrict__ 
   }
 }
 
-constexpr int COL_THREADS = 128;
+constexpr int COL_LANES = 32;     // packed rows (patches) per CTA
+constexpr int COL_TGROUPS = 8;    // MC samples are strided over 8 warps, then merged in a fixed order
+constexpr int COL_THREADS = COL_LANES * COL_TGROUPS;
 
-// grid.x < col_blocks: one thread per (c, packed row): Welford over t of A[t,c,row] (+ optional A store)
+// grid.x < col_blocks: CTA = 32 packed rows x one head; warp g runs Welford over the samples
+//   t = g, g+8, ... of A[t,c,row] (coalesced along the patch axis, 8 independent chains per row),
+//   then the 8 partial (count, mean, M2) are merged with Chan's formula in warp order 0..7
+//   (deterministic).  Optionally stores A.
 // grid.x >= col_blocks: one warp per bag: mean / M2 over t of softmax_c(Y[bag][t][:])
 __global__ void __launch_bounds__(COL_THREADS)
 welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__ rowstat,
@@ -73,27 +78,47 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
                     int n_bags, int T, int C, int R, int Rp, int col_blocks,
                     float* __restrict__ A, float* __restrict__ attn_mean, float* __restrict__ attn_m2,
                     float* __restrict__ prob_mean, float* __restrict__ prob_m2) {
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   if ((int)blockIdx.x < col_blocks) {
+    __shared__ float s_mean[COL_TGROUPS][COL_LANES], s_m2[COL_TGROUPS][COL_LANES];
     const int c = blockIdx.y;
-    const int g = blockIdx.x * COL_THREADS + threadIdx.x;
-    if (g >= R) return;
-    const int b = row2bag[g];
+    const int g = blockIdx.x * COL_LANES + lane;
     float mean = 0.f, m2 = 0.f;
-    for (int t = 0; t < T; ++t) {
-      const float2 rs = rowstat[((size_t)t * C + c) * n_bags + b];
-      const float a = __expf(logits[((size_t)t * C + c) * Rp + g] - rs.x) * rs.y;
-      if (A) A[((size_t)t * C + c) * R + g] = a;
-      const float dlt = a - mean;
-      mean += __fdividef(dlt, (float)(t + 1));
-      m2 = fmaf(dlt, a - mean, m2);
+    int cnt = 0;
+    if (g < R) {
+      const int b = row2bag[g];
+#pragma unroll 4
+      for (int t = grp; t < T; t += COL_TGROUPS) {
+        const float2 rs = __ldg(rowstat + ((size_t)t * C + c) * n_bags + b);
+        const float a = __expf(__ldg(logits + ((size_t)t * C + c) * Rp + g) - rs.x) * rs.y;
+        if (A) A[((size_t)t * C + c) * R + g] = a;
+        ++cnt;
+        const float dlt = a - mean;
+        mean += __fdividef(dlt, (float)cnt);
+        m2 = fmaf(dlt, a - mean, m2);
+      }
     }
-    if (attn_mean) attn_mean[(size_t)c * R + g] = mean;
-    if (attn_m2) attn_m2[(size_t)c * R + g] = m2;
+    s_mean[grp][lane] = mean; s_m2[grp][lane] = m2;
+    __syncthreads();
+    if (grp == 0 && g < R) {
+      float n_a = (float)cnt;          // group 0 always has the most samples
+#pragma unroll
+      for (int k = 1; k < COL_TGROUPS; ++k) {
+        const int nk = (T - k + COL_TGROUPS - 1) / COL_TGROUPS;   // samples of group k
+        if (nk <= 0) continue;
+        const float n_b = (float)nk, mb = s_mean[k][lane], qb = s_m2[k][lane];
+        const float n_ab = n_a + n_b, dlt = mb - mean;
+        mean += dlt * __fdividef(n_b, n_ab);
+        m2 += qb + dlt * dlt * __fdividef(n_a * n_b, n_ab);
+        n_a = n_ab;
+      }
+      if (attn_mean) attn_mean[(size_t)c * R + g] = mean;
+      if (attn_m2) attn_m2[(size_t)c * R + g] = m2;
+    }
   } else {
     if (blockIdx.y != 0 || prob_mean == nullptr) return;
-    const int b = ((int)blockIdx.x - col_blocks) * (COL_THREADS / 32) + (threadIdx.x >> 5);
+    const int b = ((int)blockIdx.x - col_blocks) * COL_TGROUPS + grp;
     if (b >= n_bags) return;
-    const int lane = threadIdx.x & 31;
     const float* y = Y + (size_t)b * T * C;
     float s[MAXC] = {0.f, 0.f, 0.f, 0.f};
     for (int t = lane; t < T; t += 32) {
@@ -124,8 +149,8 @@ cudaError_t launch_reduce(const Plan& p, const float* logits, const float* score
   softmax_rows_kernel<<<p.n_bags * p.T * p.C, ROW_THREADS, 0, st>>>(logits, scores, p.d_cu, p.n_bags, p.T, p.C,
                                                                     p.Rp, rowstat, Y);
   if (launches) ++*launches;
-  const int col_blocks = (p.R + COL_THREADS - 1) / COL_THREADS;
-  const int bag_blocks = (p.n_bags + COL_THREADS / 32 - 1) / (COL_THREADS / 32);
+  const int col_blocks = (p.R + COL_LANES - 1) / COL_LANES;
+  const int bag_blocks = (p.n_bags + COL_TGROUPS - 1) / COL_TGROUPS;
   welford_cols_kernel<<<dim3(col_blocks + bag_blocks, p.C), COL_THREADS, 0, st>>>(
       logits, rowstat, p.d_row2bag, Y, p.n_bags, p.T, p.C, p.R, p.Rp, col_blocks, A, attn_mean, attn_m2,
       prob_mean, prob_m2);
