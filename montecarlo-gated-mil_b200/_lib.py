@@ -10,7 +10,8 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libmcmil_b200.so")
+# MCMIL_LIB_PATH: A/B experiments with alternative builds of the same C ABI (tools/build_variants.py)
+LIB_PATH = os.environ.get("MCMIL_LIB_PATH") or os.path.join(HERE, "lib", "libmcmil_b200.so")
 HEADER_PATH = os.path.join(HERE, "..", "include", "mcmil_b200.h")
 
 IMPL_TCGEN05 = 0

@@ -84,6 +84,32 @@ __device__ __forceinline__ uint32_t keep_mask2(uint32_t r, uint32_t thr2) {
   asm("set.geu.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(thr2));
   return m;
 }
+// Same predicate with ALU-pipe integer ops only (HSET2 shares the fmaheavy pipe with the Philox
+// wide multiplies): set bit 15 of both lanes, subtract the thresholds (no borrow can cross lanes),
+// replicate each lane's bit 15 over the lane with one PRMT.
+__device__ __forceinline__ uint32_t keep_mask2_alu(uint32_t r, uint32_t thr2) {
+  const uint32_t b = (r | 0x80008000u) - thr2;
+  uint32_t m;
+  asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(m) : "r"(b));
+  return m;
+}
+#ifndef MCMIL_MASK_RECIPE
+#define MCMIL_MASK_RECIPE 0      // 0: HSET2 for all four words, 1: ALU for all, 2: two and two
+#endif
+__device__ __forceinline__ uint4 apply_keep(const uint4& h, const uint4& r, uint32_t thr2) {
+  uint4 o;
+#if MCMIL_MASK_RECIPE == 0
+  o.x = h.x & keep_mask2(r.x, thr2); o.y = h.y & keep_mask2(r.y, thr2);
+  o.z = h.z & keep_mask2(r.z, thr2); o.w = h.w & keep_mask2(r.w, thr2);
+#elif MCMIL_MASK_RECIPE == 1
+  o.x = h.x & keep_mask2_alu(r.x, thr2); o.y = h.y & keep_mask2_alu(r.y, thr2);
+  o.z = h.z & keep_mask2_alu(r.z, thr2); o.w = h.w & keep_mask2_alu(r.w, thr2);
+#else
+  o.x = h.x & keep_mask2(r.x, thr2); o.y = h.y & keep_mask2_alu(r.y, thr2);
+  o.z = h.z & keep_mask2(r.z, thr2); o.w = h.w & keep_mask2_alu(r.w, thr2);
+#endif
+  return o;
+}
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -110,6 +136,10 @@ __device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tbuf
           }
         }
       }
+#ifdef MCMIL_EXP_NO_EPI_MATH
+      acc[0] += __uint_as_float(v[0] ^ u[0]);
+      continue;
+#endif
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int d = 64 * part + 32 * HALF + 16 * j + i;
@@ -185,6 +215,9 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       const uint64_t bdesc0 = umma_desc_sw128(sbase + SM_W);
       const uint32_t da = tmem_u + q * TM_BUF_STRIDE + TM_A, db = tmem_u + q * TM_BUF_STRIDE + TM_B;
       uint32_t j = 0;                                           // this warp's sample counter
+#ifdef MCMIL_EXP_PRODUCER_ONLY
+      if (true) goto exp_skip_mma;
+#endif
       for (long long u = u_begin + q; u < u_end; u += 2, ++j) {
         mbar_wait(bar_addr(sbase, B_TEMPTY + q), (j & 1) ^ 1);
         tc_fence_after();
@@ -208,6 +241,9 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         if (elect_one()) umma_commit_cg2_mc(bar_addr(sbase, B_TFULL + q), 3);
         __syncwarp();
       }
+#ifdef MCMIL_EXP_PRODUCER_ONLY
+      exp_skip_mma:;
+#endif
     }
   } else if (warp >= PRODUCER_WARP0) {
     // ------------------------------------------------------------ producers: masked A slices
@@ -271,17 +307,21 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 #pragma unroll
         for (int si = 0; si < 4; ++si) {
           const int s = 2 * si + team;
+#ifndef MCMIL_EXP_PRODUCER_ONLY
           if (tc > 0) mbar_wait(bar_addr(sbase, B_EMPTY + empty_set + s), empty_parity);
+#endif
           uint4 nxt[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint4 h = hreg[si][i];
             uint4 o;
             if constexpr (!INJECT) {
-              o.x = h.x & keep_mask2(rnd[i].x, thr2);
-              o.y = h.y & keep_mask2(rnd[i].y, thr2);
-              o.z = h.z & keep_mask2(rnd[i].z, thr2);
-              o.w = h.w & keep_mask2(rnd[i].w, thr2);
+#ifdef MCMIL_EXP_NO_MASK
+              o = h;
+              asm volatile("" :: "r"(rnd[i].x), "r"(rnd[i].y), "r"(rnd[i].z), "r"(rnd[i].w));
+#else
+              o = apply_keep(h, rnd[i], thr2);
+#endif
             } else {
               const int trow = (int)rank * HALF_ROWS + rowi[i];
               uint32_t bits = 0;
@@ -320,7 +360,11 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     const uint32_t tempty_leader = mapa(bar_addr(sbase, B_TEMPTY), 0);
     float* xch = reinterpret_cast<float*>(smem + SM_XCH);
     uint32_t tc = 0;
+#ifdef MCMIL_EXP_PRODUCER_ONLY
+    for (long long u = u_end; u < u_end;) {
+#else
     for (long long u = u_begin; u < u_end;) {
+#endif
       const int ti = (int)(u / P.T);
       const int t_begin = (int)(u - (long long)ti * P.T);
       const long long u_next = (long long)(ti + 1) * P.T;
