@@ -211,8 +211,9 @@ def run_ours(args):
 
     merged_T = [T]
 
-    def step(i):
-        r = mm.mc_head(w, H, T, seed=i, cu_seqlens=cu, bag_ids=bag_ids, t_offset=t_offset)
+    def step(i, rounds=None):
+        r = mm.mc_head(w, H, T, seed=i, cu_seqlens=cu, bag_ids=bag_ids, t_offset=t_offset,
+                       philox_rounds=rounds or args.philox_rounds)
         if args.workload == "config4" and world > 1:
             _, _, merged_T[0] = MD.allreduce_welford([r.attn_mean, r.prob_mean], [r.attn_m2, r.prob_m2], T)
         return r
@@ -259,6 +260,26 @@ def run_ours(args):
                 "frac_of_sustained": achieved / peak_sust, "kernel_ms": k_ms, "kernel_launches": prof_k.value,
                 "kernel_share_of_step": prof_ms.value / ms_total if ms_total > 0 else None, "traffic": None}
 
+    # ---- the same step with Philox4x32-7 masks (optional fast mode; not the headline)
+    philox7 = None
+    if args.philox_rounds == 10 and not args.no_extras:
+        for i in range(3):
+            step(i, 7)
+        barrier()
+        _lib.check(lib.mcmil_profile_begin(args.steps), "mcmil_profile_begin")
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            step(300 + i, 7)
+        f1.record()
+        barrier()
+        p7_ms, p7_k = ctypes.c_double(0), ctypes.c_int(0)
+        _lib.check(lib.mcmil_profile_end(ctypes.byref(p7_ms), ctypes.byref(p7_k)), "mcmil_profile_end")
+        ms7 = f0.elapsed_time(f1)
+        k7 = p7_ms.value / max(p7_k.value, 1)
+        philox7 = {"bags_per_s_this_rank": n_bags * args.steps / (ms7 / 1e3),
+                   "kernel_ms": k7, "roofline_frac": (flops_step / S) / (k7 * 1e-3) / 1e12 / peak if k7 > 0 else None}
+
     # ---- e2e: pinned-host features in, results out, through the public API, inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -285,7 +306,7 @@ def run_ours(args):
                     hb.copy_(H_host[r0:r1], non_blocking=True)
                     r = mm.mc_head(w, hb, T, seed=i, cu_seqlens=cu[b0:b1 + 1] - cu[b0],
                                    bag_ids=None if bag_ids is None else bag_ids[b0:b1], bag_offset=b0,
-                                   t_offset=t_offset)
+                                   t_offset=t_offset, philox_rounds=args.philox_rounds)
                     outY[b0:b1].copy_(r.Y, non_blocking=True)
                     outP[0, b0:b1].copy_(r.prob_mean, non_blocking=True)
                     outP[1, b0:b1].copy_(r.prob_m2, non_blocking=True)
@@ -312,7 +333,7 @@ def run_ours(args):
 
     # ---- single-bag call latency / back-to-back throughput (the reference's bs=1 usage)
     single = None
-    if args.workload == "config2" and rank == 0:
+    if args.workload == "config2" and rank == 0 and not args.no_extras:
         nb = min(n_bags, 128)
         for i in range(10):
             mm.mc_head(w, H[(i % nb) * 1024:(i % nb + 1) * 1024], T, seed=i)
@@ -353,6 +374,7 @@ def run_ours(args):
                        "parallelism": "bags sharded over ranks, no collective" if args.workload != "config4"
                        else "MC samples sharded over ranks, one NCCL allreduce of Welford partials"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "single_bag": single,
+            "philox_rounds": args.philox_rounds, "philox7_mode": philox7,
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "clocks": clocks, "flops_per_step_per_gpu": flops_step,
         }
@@ -373,6 +395,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--e2e-chunk", type=int, default=32)
     ap.add_argument("--cpu-bags", type=int, default=8)
+    ap.add_argument("--philox-rounds", type=int, default=10, choices=[7, 10])
+    ap.add_argument("--no-extras", action="store_true", help="skip the Philox-7 and single-bag extras")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -82,6 +82,8 @@ int mcmil_plan_total_rows(const mcmil_plan_t* p);
  *   t_offset     global index of this call's first MC sample (MC-sample sharding)
  *   bag_offset   added to every bag id — both offsets only key the RNG
  *   seed         Philox key; masks are a pure function of (seed, bag, t, n, l)
+ *   philox_rounds  10 = Philox4x32-10 (what ATen / cuRAND use; default), 7 = Philox4x32-7 (the
+ *                smallest Crush-resistant round count; ~25 % faster projection kernel)
  *   p_f, p_a     feature / logit dropout probabilities (model.py:141-142)
  *   inj_feat_keep_bits  DEVICE uint32 [T][R][16]   nullable; bit l%32 of word l/32: 1 = keep
  *   inj_attn_keep_bits  DEVICE uint32 [T][C][ceil(R/32)] nullable; bit r%32 of word r/32
@@ -96,7 +98,7 @@ int mcmil_plan_total_rows(const mcmil_plan_t* p);
  *   workspace    DEVICE, >= mcmil_plan_workspace_bytes(plan), 1024-byte aligned
  */
 int mcmil_head_forward(const mcmil_weights_t* w, const mcmil_plan_t* plan, const float* H,
-                       int t_offset, int bag_offset, uint64_t seed, float p_f, float p_a,
+                       int t_offset, int bag_offset, uint64_t seed, int philox_rounds, float p_f, float p_a,
                        const uint32_t* inj_feat_keep_bits, const uint32_t* inj_attn_keep_bits,
                        int impl, float* Y, float* A, float* prob_mean, float* prob_m2,
                        float* attn_mean, float* attn_m2, void* workspace, size_t workspace_bytes,
@@ -115,7 +117,8 @@ int mcmil_welford_unpack(const double* packed, int n, float* mean, float* m2, vo
  * reference module the very same masks --------------------------------------------------
  *   feat_bits DEVICE uint32 [T][R][16], attn_bits DEVICE uint32 [T][C][ceil(R/32)] */
 int mcmil_export_masks(const mcmil_plan_t* plan, int t_offset, int bag_offset, uint64_t seed,
-                       float p_f, float p_a, uint32_t* feat_bits, uint32_t* attn_bits, void* stream);
+                       int philox_rounds, float p_f, float p_a, uint32_t* feat_bits, uint32_t* attn_bits,
+                       void* stream);
 
 /* ---- debug (tests only; not a reference-facing entry point): feature packing + tcgen05
  * projection only; dumps every CTA's raw TMEM accumulators of its first (tile, sample):

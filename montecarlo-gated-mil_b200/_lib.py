@@ -30,11 +30,11 @@ SIGNATURES = {
     "mcmil_plan_destroy": (_i, [_vp]),
     "mcmil_plan_workspace_bytes": (_sz, [_vp]),
     "mcmil_plan_total_rows": (_i, [_vp]),
-    "mcmil_head_forward": (_i, [_vp, _vp, _vp, _i, _i, _u64, _f, _f, _vp, _vp, _i,
+    "mcmil_head_forward": (_i, [_vp, _vp, _vp, _i, _i, _u64, _i, _f, _f, _vp, _vp, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mcmil_welford_pack": (_i, [_vp, _vp, _dbl, _i, _vp, _vp]),
     "mcmil_welford_unpack": (_i, [_vp, _i, _vp, _vp, _vp]),
-    "mcmil_export_masks": (_i, [_vp, _i, _i, _u64, _f, _f, _vp, _vp, _vp]),
+    "mcmil_export_masks": (_i, [_vp, _i, _i, _u64, _i, _f, _f, _vp, _vp, _vp]),
     "mcmil_debug_proj_tc": (_i, [_vp, _vp, _vp, _i, _i, _u64, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mcmil_last_launch_count": (_i, []),
     "mcmil_profile_begin": (_i, [_i]),

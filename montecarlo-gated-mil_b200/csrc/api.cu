@@ -32,7 +32,7 @@ template <class T>
 cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)); }
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-MaskSpec make_mask_spec(int t_offset, int bag_offset, uint64_t seed, float p_f, float p_a,
+MaskSpec make_mask_spec(int t_offset, int bag_offset, uint64_t seed, int rounds, float p_f, float p_a,
                         const uint32_t* inj_f, const uint32_t* inj_a) {
   MaskSpec m;
   m.key = philox_key(seed);
@@ -42,6 +42,7 @@ MaskSpec make_mask_spec(int t_offset, int bag_offset, uint64_t seed, float p_f, 
   m.sa = drop_scale(p_a);
   m.t_offset = t_offset;
   m.bag_offset = bag_offset;
+  m.rounds = rounds;
   m.inj_feat = inj_f;
   m.inj_attn = inj_a;
   return m;
@@ -150,7 +151,7 @@ size_t mcmil_plan_workspace_bytes(const mcmil_plan_t* p) { return p ? p->ws_byte
 int mcmil_plan_total_rows(const mcmil_plan_t* p) { return p ? p->R : 0; }
 
 int mcmil_head_forward(const mcmil_weights_t* w, const mcmil_plan_t* plan, const float* H,
-                       int t_offset, int bag_offset, uint64_t seed, float p_f, float p_a,
+                       int t_offset, int bag_offset, uint64_t seed, int philox_rounds, float p_f, float p_a,
                        const uint32_t* inj_feat, const uint32_t* inj_attn, int impl,
                        float* Y, float* A, float* prob_mean, float* prob_m2, float* attn_mean, float* attn_m2,
                        void* workspace, size_t workspace_bytes, void* stream) {
@@ -161,6 +162,8 @@ int mcmil_head_forward(const mcmil_weights_t* w, const mcmil_plan_t* plan, const
     return fail(MCMIL_E_BADARG, "mcmil_head_forward: inject both masks or neither");
   if (!(p_f >= 0.f && p_f <= 1.f) || !(p_a >= 0.f && p_a <= 1.f))
     return fail(MCMIL_E_BADARG, "mcmil_head_forward: dropout probability outside [0,1]");
+  if (philox_rounds != 7 && philox_rounds != 10)
+    return fail(MCMIL_E_BADARG, "mcmil_head_forward: philox_rounds must be 10 (default) or 7");
   if (workspace_bytes < plan->ws_bytes) return fail(MCMIL_E_WORKSPACE, "mcmil_head_forward: workspace too small");
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023u) != 0)
     return fail(MCMIL_E_WORKSPACE, "mcmil_head_forward: workspace must be 1024-byte aligned");
@@ -172,7 +175,7 @@ int mcmil_head_forward(const mcmil_weights_t* w, const mcmil_plan_t* plan, const
   float* logits = reinterpret_cast<float*>(ws + plan->off_logit);
   float* scores = reinterpret_cast<float*>(ws + plan->off_score);
   float2* rowstat = reinterpret_cast<float2*>(ws + plan->off_rowstat);
-  const MaskSpec m = make_mask_spec(t_offset, bag_offset, seed, p_f, p_a, inj_feat, inj_attn);
+  const MaskSpec m = make_mask_spec(t_offset, bag_offset, seed, philox_rounds, p_f, p_a, inj_feat, inj_attn);
   cudaError_t e;
   if (impl == MCMIL_IMPL_TCGEN05) {
     const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
@@ -203,7 +206,7 @@ int mcmil_debug_proj_tc(const mcmil_weights_t* w, const mcmil_plan_t* plan, cons
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   float* logits = reinterpret_cast<float*>(ws + plan->off_logit);
   float* scores = reinterpret_cast<float*>(ws + plan->off_score);
-  const MaskSpec m = make_mask_spec(t_offset, bag_offset, seed, p_f, p_a, inj_feat, inj_attn);
+  const MaskSpec m = make_mask_spec(t_offset, bag_offset, seed, 10, p_f, p_a, inj_feat, inj_attn);
   int launches = 0;
   cudaError_t e = launch_proj_tc(*w, *plan, m, H, logits, scores, dbg, st, &launches);
   const size_t plane = (size_t)plan->T * plan->C * plan->Rp * sizeof(float);
@@ -251,10 +254,11 @@ int mcmil_welford_unpack(const double* packed, int n, float* mean, float* m2, vo
   return e == cudaSuccess ? 0 : cuda_fail(e, "mcmil_welford_unpack");
 }
 
-int mcmil_export_masks(const mcmil_plan_t* plan, int t_offset, int bag_offset, uint64_t seed, float p_f,
-                       float p_a, uint32_t* feat_bits, uint32_t* attn_bits, void* stream) {
+int mcmil_export_masks(const mcmil_plan_t* plan, int t_offset, int bag_offset, uint64_t seed, int philox_rounds,
+                       float p_f, float p_a, uint32_t* feat_bits, uint32_t* attn_bits, void* stream) {
   if (!plan) return fail(MCMIL_E_BADARG, "mcmil_export_masks: null plan");
-  const MaskSpec m = make_mask_spec(t_offset, bag_offset, seed, p_f, p_a, nullptr, nullptr);
+  if (philox_rounds != 7 && philox_rounds != 10) return fail(MCMIL_E_BADARG, "mcmil_export_masks: philox_rounds must be 10 or 7");
+  const MaskSpec m = make_mask_spec(t_offset, bag_offset, seed, philox_rounds, p_f, p_a, nullptr, nullptr);
   cudaError_t e = launch_export_masks(*plan, m, feat_bits, attn_bits, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "mcmil_export_masks");
 }

@@ -43,6 +43,7 @@ struct MaskSpec {
   uint32_t thr_f, thr_a;
   float sf, sa;          // 1/(1-p)
   int t_offset, bag_offset;
+  int rounds;            // Philox rounds: 10 (default) or 7
   const uint32_t* inj_feat;   // [T][R][16] or null
   const uint32_t* inj_attn;   // [T][C][Rp/32] or null
 };

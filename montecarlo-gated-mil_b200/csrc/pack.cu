@@ -111,7 +111,7 @@ __global__ void export_feat_kernel(const int32_t* __restrict__ cu, const int32_t
     uint32_t out = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      out |= feature_keep8((uint32_t)(wd * 4 + j), n, (uint32_t)(m.t_offset + t), (uint32_t)(m.bag_offset + gbag[b]),
+      out |= feature_keep8(m.rounds, (uint32_t)(wd * 4 + j), n, (uint32_t)(m.t_offset + t), (uint32_t)(m.bag_offset + gbag[b]),
                            m.key, m.thr_f) << (8 * j);
     bits[i] = out;
   }
@@ -130,7 +130,7 @@ __global__ void export_attn_kernel(const int32_t* __restrict__ cu, const int32_t
       const int g = wd * 32 + j;
       if (g >= R) break;
       const int b = row2bag[g];
-      const uint4 r = attn_words((uint32_t)(c >> 2), (uint32_t)(g - cu[b]), (uint32_t)(m.t_offset + t),
+      const uint4 r = attn_words_rt(m.rounds, (uint32_t)(c >> 2), (uint32_t)(g - cu[b]), (uint32_t)(m.t_offset + t),
                                  (uint32_t)(m.bag_offset + gbag[b]), m.key);
       out |= (attn_keep_from(r, c, m.thr_a) ? 1u : 0u) << j;
     }

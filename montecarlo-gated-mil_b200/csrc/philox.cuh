@@ -11,25 +11,25 @@ constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 constexpr uint32_t ATTN_CHUNK_BASE = 64u;  // ctr.x >= 64: logit-dropout slots
 
-#ifndef MCMIL_PHILOX_ROUNDS
-#define MCMIL_PHILOX_ROUNDS 10
-#endif
+constexpr int PHILOX_MAX_ROUNDS = 10;   // Philox4x32-10 (Random123 / cuRAND / ATen default); 7 is the
+                                        // smallest Crush-resistant round count (Salmon et al., SC'11)
 
-struct PhiloxKey { uint32_t k0[MCMIL_PHILOX_ROUNDS], k1[MCMIL_PHILOX_ROUNDS]; };
+struct PhiloxKey { uint32_t k0[PHILOX_MAX_ROUNDS], k1[PHILOX_MAX_ROUNDS]; };
 
 __host__ __device__ inline PhiloxKey philox_key(uint64_t seed) {
   PhiloxKey k;
   uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
-  for (int r = 0; r < MCMIL_PHILOX_ROUNDS; ++r) { k.k0[r] = a; k.k1[r] = b; a += PHILOX_W0; b += PHILOX_W1; }
+  for (int r = 0; r < PHILOX_MAX_ROUNDS; ++r) { k.k0[r] = a; k.k1[r] = b; a += PHILOX_W0; b += PHILOX_W1; }
   return k;
 }
 
 // Round keys are pre-expanded on the host (they only depend on the seed) so each round is
 // 2 wide multiplies + 2 three-input XORs.
+template <int ROUNDS>
 __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                             const PhiloxKey& key) {
 #pragma unroll
-  for (int r = 0; r < MCMIL_PHILOX_ROUNDS; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
     const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.k0[r];
@@ -38,11 +38,16 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
   }
   return make_uint4(c0, c1, c2, c3);
 }
+// runtime round count (7 or 10) for the non-critical kernels
+__device__ __forceinline__ uint4 philox4x32_rt(int rounds, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               const PhiloxKey& key) {
+  return rounds == 7 ? philox4x32<7>(c0, c1, c2, c3, key) : philox4x32<10>(c0, c1, c2, c3, key);
+}
 
 // keep-bits (bit e = keep element 8q+e) of one feature chunk
-__device__ __forceinline__ uint32_t feature_keep8(uint32_t q, uint32_t n, uint32_t t, uint32_t bag,
+__device__ __forceinline__ uint32_t feature_keep8(int rounds, uint32_t q, uint32_t n, uint32_t t, uint32_t bag,
                                                    const PhiloxKey& key, uint32_t thr) {
-  const uint4 r = philox4x32(q, n, t, bag, key);
+  const uint4 r = philox4x32_rt(rounds, q, n, t, bag, key);
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
   uint32_t bits = 0;
 #pragma unroll
@@ -54,9 +59,14 @@ __device__ __forceinline__ uint32_t feature_keep8(uint32_t q, uint32_t n, uint32
 }
 
 // keep flag of the logit of (bag, t, n), head c
+template <int ROUNDS>
 __device__ __forceinline__ uint4 attn_words(uint32_t group, uint32_t n, uint32_t t, uint32_t bag,
                                             const PhiloxKey& key) {
-  return philox4x32(ATTN_CHUNK_BASE + group, n, t, bag, key);
+  return philox4x32<ROUNDS>(ATTN_CHUNK_BASE + group, n, t, bag, key);
+}
+__device__ __forceinline__ uint4 attn_words_rt(int rounds, uint32_t group, uint32_t n, uint32_t t, uint32_t bag,
+                                               const PhiloxKey& key) {
+  return philox4x32_rt(rounds, ATTN_CHUNK_BASE + group, n, t, bag, key);
 }
 __device__ __forceinline__ bool attn_keep_from(const uint4& r, int c, uint32_t thr) {
   const uint32_t w = (c & 3) == 0 ? r.x : (c & 3) == 1 ? r.y : (c & 3) == 2 ? r.z : r.w;

@@ -23,7 +23,7 @@ struct SimtParams {
   const TileDesc* tiles;
   float* logits; float* scores;
   const uint32_t* inj_feat; const uint32_t* inj_attn;
-  int T, C, R, Rp, n_out, head0, t_offset, bag_offset;
+  int T, C, R, Rp, n_out, head0, t_offset, bag_offset, rounds;
   uint32_t thr_f, thr_a;
   float sf, sa;
   PhiloxKey key;
@@ -65,7 +65,7 @@ proj_simt_kernel(const SimtParams P) {
         const int q = k0 / 8 + lchunk;
         uint32_t bits;
         if (P.inj_feat == nullptr)
-          bits = feature_keep8((uint32_t)q, (uint32_t)(td.n0 + trow_l), tg, bag, P.key, P.thr_f);
+          bits = feature_keep8(P.rounds, (uint32_t)q, (uint32_t)(td.n0 + trow_l), tg, bag, P.key, P.thr_f);
         else
           bits = reinterpret_cast<const uint8_t*>(P.inj_feat)[((size_t)t * P.R + td.row0 + trow_l) * 64 + q];
 #pragma unroll
@@ -139,7 +139,7 @@ proj_simt_kernel(const SimtParams P) {
     if (trow < td.nrows) {
       const int g = td.row0 + trow;
       uint4 rnd = make_uint4(0, 0, 0, 0);
-      if (P.inj_attn == nullptr) rnd = attn_words(0u, (uint32_t)(td.n0 + trow), tg, bag, P.key);
+      if (P.inj_attn == nullptr) rnd = attn_words_rt(P.rounds, 0u, (uint32_t)(td.n0 + trow), tg, bag, P.key);
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
         if (c < P.n_out) {
@@ -178,6 +178,7 @@ cudaError_t launch_proj_simt(const Weights& w, const Plan& p, const MaskSpec& m,
     P.t_offset = m.t_offset; P.bag_offset = m.bag_offset;
     P.thr_f = m.thr_f; P.thr_a = m.thr_a; P.sf = m.sf; P.sa = m.sa;
     P.key = m.key;
+    P.rounds = m.rounds;
     // blockIdx.y is limited to 65535: chunk T if ever needed
     for (int t0 = 0; t0 < p.T; t0 += 32768) {
       SimtParams Q = P;

@@ -23,9 +23,14 @@
 namespace mcmil {
 using namespace ptx;
 
-constexpr int TC_THREADS = 14 * 32;
-constexpr int PRODUCER_WARP0 = 4, MMA_WARP = 12, LOAD_WARP = 13;   // warps 4..11 produce
-constexpr int TEAM_WARPS = 4;                    // two teams of four producer warps
+#ifndef MCMIL_TEAMS
+#define MCMIL_TEAMS 4
+#endif
+constexpr int TEAMS = MCMIL_TEAMS;               // producer teams: team k fills the K-slices s = k (mod TEAMS)
+constexpr int TEAM_WARPS = 4;                    // warps per team (16 patch rows each)
+constexpr int TEAM_SLICES = NSLICE / TEAMS;      // slices per team and sample
+constexpr int PRODUCER_WARP0 = 4, MMA_WARP = PRODUCER_WARP0 + TEAMS * TEAM_WARPS, LOAD_WARP = MMA_WARP + 1;
+constexpr int TC_THREADS = (LOAD_WARP + 1) * 32;
 
 constexpr uint32_t SM_W = 0;
 constexpr uint32_t SM_RING = SM_W + NSLICE * SLICE_BYTES_W;        // 139264: 8 slots x 8 KB
@@ -153,7 +158,7 @@ __device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tbuf
   }
 }
 
-template <int NOUT, bool INJECT, bool DEBUG>
+template <int NOUT, bool INJECT, bool DEBUG, int ROUNDS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 proj_tc_kernel(const __grid_constant__ ProjParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -252,7 +257,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     // SM sub-partition belong to different teams.  The ring is a full sample deep (slot = K-slice),
     // so a warp only ever waits for the MMAs of the PREVIOUS sample.
     const int pw = warp - PRODUCER_WARP0;
-    const int team = pw >> 2, wt = pw & 3;
+    const int team = pw >> 2, wt = pw & 3;           // warps of one team sit on the four different schedulers
     const uint32_t full_leader = mapa(bar_addr(sbase, B_FULL), 0);
     const uint32_t thr2 = P.thr_f | (P.thr_f << 16);
     const int chunk = lane & 7;
@@ -271,18 +276,18 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       const TileDesc td = P.tiles[ti];
       const uint32_t bag = (uint32_t)(P.bag_offset + td.gbag);
       // this thread's 16 chunks (4 slices of its team x 4 row slots) of the fp16 feature tile: registers
-      uint4 hreg[4][4];
+      uint4 hreg[TEAM_SLICES][4];
       uint32_t nrow[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int trow = (int)rank * HALF_ROWS + rowi[i];
         nrow[i] = (uint32_t)(td.n0 + trow);
 #pragma unroll
-        for (int si = 0; si < 4; ++si) {
+        for (int si = 0; si < TEAM_SLICES; ++si) {
           uint4 packed = make_uint4(0, 0, 0, 0);
           if (trow < td.nrows) {
             const float4* src = reinterpret_cast<const float4*>(
-                P.H + (size_t)(td.row0 + trow) * L + (2 * si + team) * KSLICE + chunk * 8);
+                P.H + (size_t)(td.row0 + trow) * L + (TEAMS * si + team) * KSLICE + chunk * 8);
             const float4 a = __ldg(src), b = __ldg(src + 1);
             packed.x = pack_half2(a.x, a.y); packed.y = pack_half2(a.z, a.w);
             packed.z = pack_half2(b.x, b.y); packed.w = pack_half2(b.z, b.w);
@@ -296,7 +301,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       if constexpr (!INJECT) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          rnd[i] = philox4x32((uint32_t)(team * 8 + chunk), nrow[i], (uint32_t)(P.t_offset + t_begin), bag, P.key);
+          rnd[i] = philox4x32<ROUNDS>((uint32_t)(team * 8 + chunk), nrow[i], (uint32_t)(P.t_offset + t_begin), bag, P.key);
       }
 #pragma unroll 1
       for (int t = t_begin; t < t_end; ++t, ++tc) {
@@ -305,8 +310,8 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         const uint32_t empty_set = ((tc + 1) & 1) * NSLICE, empty_parity = ((tc - 1) >> 1) & 1;
         const uint32_t full_set = (tc & 1) * NSLICE;
 #pragma unroll
-        for (int si = 0; si < 4; ++si) {
-          const int s = 2 * si + team;
+        for (int si = 0; si < TEAM_SLICES; ++si) {
+          const int s = TEAMS * si + team;
 #ifndef MCMIL_EXP_PRODUCER_ONLY
           if (tc > 0) mbar_wait(bar_addr(sbase, B_EMPTY + empty_set + s), empty_parity);
 #endif
@@ -335,11 +340,11 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
             *reinterpret_cast<uint4*>(smem + SM_RING + s * SLICE_BYTES_A + off[i]) = o;
           }
           if constexpr (!INJECT) {
-            // next slice of this team: (s + 2, t), or (team, t + 1) after the last one of the sample
-            const uint32_t q_next = (uint32_t)((si < 3 ? s + 2 : team) * 8 + chunk);
-            const uint32_t t_next = si < 3 ? tg : tg + 1u;
+            // next slice of this team: (s + TEAMS, t), or (team, t + 1) after the last one of the sample
+            const uint32_t q_next = (uint32_t)((si < TEAM_SLICES - 1 ? s + TEAMS : team) * 8 + chunk);
+            const uint32_t t_next = si < TEAM_SLICES - 1 ? tg : tg + 1u;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) nxt[i] = philox4x32(q_next, nrow[i], t_next, bag, P.key);
+            for (int i = 0; i < 4; ++i) nxt[i] = philox4x32<ROUNDS>(q_next, nrow[i], t_next, bag, P.key);
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -408,7 +413,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
           const uint32_t tg = (uint32_t)(P.t_offset + t);
           uint4 rnd = make_uint4(0, 0, 0, 0);
           if constexpr (!INJECT)
-            rnd = attn_words(0u, (uint32_t)(td.n0 + trow), tg, (uint32_t)(P.bag_offset + td.gbag), P.key);
+            rnd = attn_words<ROUNDS>(0u, (uint32_t)(td.n0 + trow), tg, (uint32_t)(P.bag_offset + td.gbag), P.key);
 #pragma unroll
           for (int c = 0; c < NOUT; ++c) {
             const int head = P.head0 + c;
@@ -440,24 +445,30 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const float* H,
                            float* logits, float* scores, float* dbg, cudaStream_t st, int* launches) {
   using KernelFn = void (*)(ProjParams);
-  static const KernelFn kernels[2][4] = {
-      {proj_tc_kernel<1, false, false>, proj_tc_kernel<2, false, false>, proj_tc_kernel<3, false, false>,
-       proj_tc_kernel<4, false, false>},
-      {proj_tc_kernel<1, true, false>, proj_tc_kernel<2, true, false>, proj_tc_kernel<3, true, false>,
-       proj_tc_kernel<4, true, false>}};
-  static const KernelFn debug_kernel = proj_tc_kernel<2, false, true>;   // raw-accumulator dump (tests only)
+  // [rounds 10 / 7][in-kernel Philox / injected masks][heads per launch]
+  static const KernelFn kernels[2][2][4] = {
+      {{proj_tc_kernel<1, false, false, 10>, proj_tc_kernel<2, false, false, 10>, proj_tc_kernel<3, false, false, 10>,
+        proj_tc_kernel<4, false, false, 10>},
+       {proj_tc_kernel<1, true, false, 10>, proj_tc_kernel<2, true, false, 10>, proj_tc_kernel<3, true, false, 10>,
+        proj_tc_kernel<4, true, false, 10>}},
+      {{proj_tc_kernel<1, false, false, 7>, proj_tc_kernel<2, false, false, 7>, proj_tc_kernel<3, false, false, 7>,
+        proj_tc_kernel<4, false, false, 7>},
+       {proj_tc_kernel<1, true, false, 10>, proj_tc_kernel<2, true, false, 10>, proj_tc_kernel<3, true, false, 10>,
+        proj_tc_kernel<4, true, false, 10>}}};
+  static const KernelFn debug_kernel = proj_tc_kernel<2, false, true, 10>;   // raw-accumulator dump (tests only)
   static bool attr_set = false;
   if (!attr_set) {
-    for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 4; ++b) {
-        cudaError_t e = cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
-        if (e != cudaSuccess) return e;
-      }
+    for (int r = 0; r < 2; ++r)
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 4; ++b) {
+          cudaError_t e = cudaFuncSetAttribute(kernels[r][a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+          if (e != cudaSuccess) return e;
+        }
     cudaError_t e = cudaFuncSetAttribute(debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (dbg != nullptr && !(w.shared && w.C == 2 && m.inj_feat == nullptr)) return cudaErrorInvalidValue;
+  if (dbg != nullptr && !(w.shared && w.C == 2 && m.inj_feat == nullptr && m.rounds == 10)) return cudaErrorInvalidValue;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -481,7 +492,8 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
     P.sf = m.sf; P.hsf = 0.5f * m.sf; P.sa = m.sa;
     P.key = m.key;
     P.epi = w.epi[s];
-    const KernelFn fn = dbg != nullptr ? debug_kernel : kernels[m.inj_feat != nullptr ? 1 : 0][P.n_out - 1];
+    const KernelFn fn = dbg != nullptr ? debug_kernel
+                                       : kernels[m.rounds == 7 ? 1 : 0][m.inj_feat != nullptr ? 1 : 0][P.n_out - 1];
     fn<<<2 * n_pairs, TC_THREADS, SM_TOTAL, st>>>(P);
     if (launches) ++*launches;
     cudaError_t e = cudaGetLastError();

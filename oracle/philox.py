@@ -68,7 +68,7 @@ def _key(seed: int):
     return seed & 0xFFFFFFFF, seed >> 32
 
 
-def feature_keep(seed: int, bag: int, t0: int, T: int, N: int, p: float, L: int = 512) -> np.ndarray:
+def feature_keep(seed: int, bag: int, t0: int, T: int, N: int, p: float, L: int = 512, rounds: int = 10) -> np.ndarray:
     """keep[t, n, l] in {0,1} (uint8) for t in [t0, t0+T), n in [0, N)."""
     assert L % 8 == 0
     thr = drop_threshold(p)
@@ -77,7 +77,7 @@ def feature_keep(seed: int, bag: int, t0: int, T: int, N: int, p: float, L: int 
     q = np.arange(Q, dtype=np.uint32)[None, :]
     n = np.arange(N, dtype=np.uint32)[:, None]
     for i in range(T):
-        out = philox4x32((q, n, np.uint32(t0 + i), np.uint32(bag)), _key(seed))
+        out = philox4x32((q, n, np.uint32(t0 + i), np.uint32(bag)), _key(seed), rounds)
         lanes = np.empty((N, Q, 8), dtype=np.uint32)
         for w in range(4):
             lanes[:, :, 2 * w] = out[w] & np.uint32(0xFFFF)
@@ -86,14 +86,14 @@ def feature_keep(seed: int, bag: int, t0: int, T: int, N: int, p: float, L: int 
     return keep
 
 
-def attn_keep(seed: int, bag: int, t0: int, T: int, N: int, C: int, p: float) -> np.ndarray:
+def attn_keep(seed: int, bag: int, t0: int, T: int, N: int, C: int, p: float, rounds: int = 10) -> np.ndarray:
     """keep[t, c, n] in {0,1} (uint8)."""
     thr = drop_threshold(p)
     keep = np.empty((T, C, N), dtype=np.uint8)
     n = np.arange(N, dtype=np.uint32)[None, :]
     t = (t0 + np.arange(T, dtype=np.uint32))[:, None]
     for g in range((C + 3) // 4):
-        out = philox4x32((np.uint32(ATTN_CHUNK_BASE + g), n, t, np.uint32(bag)), _key(seed))
+        out = philox4x32((np.uint32(ATTN_CHUNK_BASE + g), n, t, np.uint32(bag)), _key(seed), rounds)
         for w in range(4):
             c = 4 * g + w
             if c < C:

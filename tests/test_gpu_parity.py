@@ -85,6 +85,29 @@ def test_exported_masks_match_numpy_philox(mm):
 
 
 @pytest.mark.parametrize("impl", IMPLS)
+def test_philox7_mode_vs_oracle(mm, impl):
+    """philox_rounds=7: exported masks equal the numpy Philox4x32-7 stream and the head matches the
+    fp64 oracle driven by those masks."""
+    dev = torch.device("cuda")
+    N, T, C, seed = 200, 6, 2, 31337
+    sd = G.make_weights(61, C, True)
+    Hn = G.make_features(700, N)
+    kf = PX.feature_keep(seed, 0, 2, T, N, 0.1, rounds=7)
+    ka = PX.attn_keep(seed, 0, 2, T, N, C, 0.1, rounds=7)
+    fb, ab = mm.export_masks(T, N, C, seed, 0.1, 0.1, t_offset=2, device=dev, philox_rounds=7)
+    assert np.array_equal(PX.unpack_bits(fb.cpu().numpy().view(np.uint32), 512), kf)
+    assert np.array_equal(PX.unpack_bits(ab.cpu().numpy().view(np.uint32), N), ka)
+    assert not np.array_equal(kf, PX.feature_keep(seed, 0, 2, T, N, 0.1, rounds=10))
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
+    res = mm.mc_head(w, torch.from_numpy(Hn).to(dev), T, seed=seed, t_offset=2, return_attention=True, impl=impl,
+                     philox_rounds=7)
+    ref = G.mc_head_oracle(sd, Hn, kf, ka, 0.1, 0.1)
+    _check(res, ref, impl, T, A_ref=ref["A"])
+    with pytest.raises(ValueError):
+        mm.mc_head(w, torch.from_numpy(Hn).to(dev), T, philox_rounds=8)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_injected_masks(mm, name, impl):
     """Masks injected (Philox-regenerated, or the reference's own torch draws for *_native):

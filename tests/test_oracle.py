@@ -19,6 +19,16 @@ def test_philox_known_answers():
     for ctr, key, want in kat:
         got = PX.philox4x32([np.uint32(c) for c in ctr], key)
         assert tuple(int(g) for g in got) == want
+    # Random123 kat_vectors, philox4x32-7 (the optional fast mode)
+    kat7 = [
+        ((0, 0, 0, 0), (0, 0), (0x5F6FB709, 0x0D893F64, 0x4F121F81, 0x4F730A48)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF), (0x5207DDC2, 0x45165E59, 0x4D8EE751, 0x8C52F662)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0x4DFCCABA, 0x190A87F0, 0xC47362BA, 0xB6B5242A)),
+    ]
+    for ctr, key, want in kat7:
+        got = PX.philox4x32([np.uint32(c) for c in ctr], key, rounds=7)
+        assert tuple(int(g) for g in got) == want
 
 
 def test_threshold_and_rates():
