@@ -14,7 +14,7 @@
 //   regs : each producer thread keeps ITS 16 chunks of the fp16 feature tile in registers for the
 //          whole work item (converted from the fp32 features once per item);
 //   TMEM : two accumulator buffers (double buffered across t).
-// Warp roles (14 warps): 0-3 epilogue (TMEM -> tanh/sigmoid/gate/w-dot -> logits),
+// Warp roles (14 warps with 2 producer teams): 0-3 epilogue (TMEM -> tanh/sigmoid/gate/w-dot -> logits),
 //   4-11 producers (Philox mask -> masked fp16 A slice, generic-proxy st.shared + proxy fence),
 //   12, 13 MMA issuers (even / odd samples; 12 owns the TMEM allocation, 13 first TMA-loads W).
 #include "internal.h"
@@ -24,7 +24,7 @@ namespace mcmil {
 using namespace ptx;
 
 #ifndef MCMIL_TEAMS
-#define MCMIL_TEAMS 4
+#define MCMIL_TEAMS 2   // 4 (16 producer warps, 80 regs/thread, small spills) measured within 2 %: profiles/r1_experiments.md
 #endif
 constexpr int TEAMS = MCMIL_TEAMS;               // producer teams: team k fills the K-slices s = k (mod TEAMS)
 constexpr int TEAM_WARPS = 4;                    // warps per team (16 patch rows each)
