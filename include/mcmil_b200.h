@@ -130,6 +130,26 @@ int mcmil_debug_proj_tc(const mcmil_weights_t* w, const mcmil_plan_t* plan, cons
                         float* dbg, float* logits_out, float* scores_out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- "next" rows of SURVEY.md §8f: the consumer and the producer either side of the head ----------
+ * mcmil_attnmap_stats replaces ImagePatcher.reconstruct_attention_map (image_patcher.py:83-110) + the
+ * mean / std over the MC passes (infer.py:212-219), at tile-boundary CELL resolution:
+ *   A          DEVICE fp32 [T][C][R] (mcmil_head_forward's A), this bag's rows start at row0
+ *   cell_ptr   DEVICE int32 [n_cells+1], cell_idx DEVICE int32 [nnz]: CSR of the bag positions
+ *              (0..n-1) of the selected patches that cover each cell
+ *   cellv_ws   DEVICE fp32 [T][C][n_cells], vmax_ws DEVICE fp32 [T][C]   (workspace)
+ *   cell_mean / cell_m2  DEVICE fp32 [C][n_cells]: Welford over t of the per-pass max-normalised
+ *              overlap-averaged attention of the cell (count = T; std = sqrt(m2/(T-1)))
+ * mcmil_tile_nonzero_pct / mcmil_gather_tiles replace the loop of ImagePatcher.convert_img_to_bag
+ * (image_patcher.py:43-59): per-tile percentage of channel-0 pixels > 0, and the gather of the selected
+ * tiles (rows of `tiles` = (y, x, h, w, i, j) as image_patcher.py:36) into a (n, channels, patch, patch) bag. */
+int mcmil_attnmap_stats(const float* A, int T, int C, int R, int row0, const int32_t* cell_ptr,
+                        const int32_t* cell_idx, int n_cells, float* cellv_ws, float* vmax_ws, float* cell_mean,
+                        float* cell_m2, void* stream);
+int mcmil_tile_nonzero_pct(const float* image /*[channels][H][W], channel 0 is read*/, int W, const int32_t* tiles,
+                           int n_tiles, int patch, float* pct, void* stream);
+int mcmil_gather_tiles(const float* image, int channels, int H, int W, const int32_t* tiles, const int32_t* selected,
+                       int n_selected, int patch, float* bag, void* stream);
+
 /* ---- measurement hook (bench.py): brackets the tcgen05 projection launch(es) of the next
  * `max_calls` mcmil_head_forward calls with CUDA events on the launching stream;
  * mcmil_profile_end synchronises them and returns the summed device time and the number of

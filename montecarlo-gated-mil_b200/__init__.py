@@ -5,7 +5,8 @@ Import as `mcmil_b200` (the repo-root alias package; this directory's name has a
 """
 from .head import HeadWeights, MCHeadResult, mc_head, export_masks  # noqa: F401
 from .model import MultiHeadGatedAttentionMIL, deactivate_batchnorm  # noqa: F401
+from .patcher import ImagePatcher, AttentionMapStats  # noqa: F401
 from . import distributed  # noqa: F401
 
 __all__ = ["HeadWeights", "MCHeadResult", "mc_head", "export_masks", "MultiHeadGatedAttentionMIL",
-           "deactivate_batchnorm", "distributed"]
+           "deactivate_batchnorm", "distributed", "ImagePatcher", "AttentionMapStats"]

@@ -37,6 +37,9 @@ SIGNATURES = {
     "mcmil_export_masks": (_i, [_vp, _i, _i, _u64, _i, _f, _f, _vp, _vp, _vp]),
     "mcmil_debug_proj_tc": (_i, [_vp, _vp, _vp, _i, _i, _u64, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mcmil_last_launch_count": (_i, []),
+    "mcmil_attnmap_stats": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "mcmil_tile_nonzero_pct": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
+    "mcmil_gather_tiles": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "mcmil_profile_begin": (_i, [_i]),
     "mcmil_profile_end": (_i, [C.POINTER(_dbl), C.POINTER(_i)]),
 }

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmcmil_b200.so")
-SOURCES = ["api.cu", "pack.cu", "proj_tc.cu", "proj_simt.cu", "reduce.cu"]
+SOURCES = ["api.cu", "pack.cu", "proj_tc.cu", "proj_simt.cu", "reduce.cu", "attnmap.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

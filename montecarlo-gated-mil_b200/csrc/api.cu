@@ -243,6 +243,34 @@ int mcmil_profile_end(double* total_ms, int* kernels) {
   return 0;
 }
 
+int mcmil_attnmap_stats(const float* A, int T, int C, int R, int row0, const int32_t* cell_ptr,
+                        const int32_t* cell_idx, int n_cells, float* cellv_ws, float* vmax_ws, float* cell_mean,
+                        float* cell_m2, void* stream) {
+  if (!A || !cell_ptr || !cell_idx || !cellv_ws || !vmax_ws || !cell_mean || !cell_m2)
+    return fail(MCMIL_E_BADARG, "mcmil_attnmap_stats: null pointer");
+  if (T < 1 || C < 1 || n_cells < 1 || row0 < 0 || R < 1) return fail(MCMIL_E_BADARG, "mcmil_attnmap_stats: bad size");
+  cudaError_t e = launch_attnmap(A, T, C, R, row0, cell_ptr, cell_idx, n_cells, cellv_ws, vmax_ws, cell_mean,
+                                 cell_m2, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "mcmil_attnmap_stats");
+}
+
+int mcmil_tile_nonzero_pct(const float* image, int W, const int32_t* tiles, int n_tiles, int patch, float* pct,
+                           void* stream) {
+  if (!image || !tiles || !pct || n_tiles < 1 || patch < 1 || W < patch)
+    return fail(MCMIL_E_BADARG, "mcmil_tile_nonzero_pct: bad argument");
+  cudaError_t e = launch_tile_nonzero(image, W, tiles, n_tiles, patch, pct, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "mcmil_tile_nonzero_pct");
+}
+
+int mcmil_gather_tiles(const float* image, int channels, int H, int W, const int32_t* tiles, const int32_t* selected,
+                       int n_selected, int patch, float* bag, void* stream) {
+  if (!image || !tiles || !selected || !bag || n_selected < 0 || channels < 1)
+    return fail(MCMIL_E_BADARG, "mcmil_gather_tiles: bad argument");
+  cudaError_t e = launch_gather_tiles(image, channels, H, W, tiles, selected, n_selected, patch, bag,
+                                      (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "mcmil_gather_tiles");
+}
+
 int mcmil_welford_pack(const float* mean, const float* m2, double count, int n, double* packed, void* stream) {
   if (!mean || !m2 || !packed || n < 0) return fail(MCMIL_E_BADARG, "mcmil_welford_pack: bad argument");
   cudaError_t e = launch_welford_pack(mean, m2, count, n, packed, (cudaStream_t)stream);

@@ -61,6 +61,13 @@ cudaError_t launch_reduce(const Plan& p, const float* logits, const float* score
                           float* attn_m2, cudaStream_t st, int* launches);
 cudaError_t launch_export_masks(const Plan& p, const MaskSpec& m, uint32_t* feat_bits, uint32_t* attn_bits,
                                 cudaStream_t st);
+cudaError_t launch_attnmap(const float* A, int T, int C, int R, int row0, const int32_t* cell_ptr,
+                           const int32_t* cell_idx, int n_cells, float* cellv, float* vmax, float* mean,
+                           float* m2, cudaStream_t st);
+cudaError_t launch_tile_nonzero(const float* img, int W, const int32_t* tiles, int n_tiles, int patch, float* pct,
+                                cudaStream_t st);
+cudaError_t launch_gather_tiles(const float* img, int Cimg, int Himg, int W, const int32_t* tiles,
+                                const int32_t* sel, int n_sel, int patch, float* bag, cudaStream_t st);
 cudaError_t launch_welford_pack(const float* mean, const float* m2, double count, int n, double* packed,
                                 cudaStream_t st);
 cudaError_t launch_welford_unpack(const double* packed, int n, float* mean, float* m2, cudaStream_t st);

@@ -272,3 +272,36 @@ def test_argument_errors(mm):
     r = mm.mc_head(w, H, 3, p_f=1.0, p_a=1.0)                # nn.Dropout(p=1): everything dropped
     assert torch.isfinite(r.Y).all() and (r.Y.abs().max().item() == 0.0)
     assert (r.attn_mean - 0.1).abs().max().item() < 1e-6     # all logits 0 -> uniform attention
+
+
+def test_config5_pipeline_small(mm):
+    """infer.py path at a small size with the REAL ResNet-18 extractor (batch-statistics BatchNorm):
+    tiling -> features once -> fused head -> attention-map statistics; head checked against the oracle
+    on the extractor's own features."""
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    model = mm.MultiHeadGatedAttentionMIL(pretrained=False, shared_attention=False)
+    model.apply(mm.deactivate_batchnorm)
+    model.to(dev).eval()
+    h, w, T = 700, 520, 8
+    from oracle import patcher_oracle as PO
+    img = torch.from_numpy(PO.synth_image(3, 3, h, w)).to(dev)
+    pt = mm.ImagePatcher(patch_size=224, overlap=0.5, bag_size=-1, empty_thresh=0.5)
+    pt.get_tiles(h, w)
+    bag, idx, _ = pt.convert_img_to_bag(img)
+    assert bag.shape[0] == len(idx) >= 4
+    Y, A = model.mc_inference(bag.unsqueeze(0), N=T, device="cuda", seed=5)
+    assert Y.shape == (T, 1, 2) and A.shape == (T, 1, 2, len(idx))
+    with torch.no_grad():
+        H = model.extract_features(bag.unsqueeze(0))
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items() if not k.startswith("feature_extractor")}
+    n = len(idx)
+    ref = G.mc_head_oracle(sd, H.cpu().numpy(), PX.feature_keep(5, 0, 0, T, n, 0.1), PX.attn_keep(5, 0, 0, T, n, 2, 0.1),
+                           0.1, 0.1)
+    assert np.abs(A[:, 0].double().cpu().numpy() - ref["A"]).max() < ATTN_ATOL
+    P = torch.softmax(Y[:, 0].double(), -1).cpu().numpy()
+    assert np.abs(P / ref["P"] - 1).max() < PROB_RTOL
+    st = pt.attention_map_stats(A, idx, (h, w))
+    mean_ref, std_ref = PO.attention_map_stats(ref["A"], pt.tiles, idx, (1, h, w))
+    assert np.abs(st.mean_map().cpu().numpy() - mean_ref[:, 0]).max() < 1e-3
+    assert np.abs(st.std_map().cpu().numpy() - std_ref[:, 0]).max() < 1e-3

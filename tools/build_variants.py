@@ -9,7 +9,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "montecarlo-gated-mil_b200", "csrc")
 OUT = os.path.join(ROOT, "build", "variants")
-SRC = ["api.cu", "pack.cu", "proj_tc.cu", "proj_simt.cu", "reduce.cu"]
+SRC = ["api.cu", "pack.cu", "proj_tc.cu", "proj_simt.cu", "reduce.cu", "attnmap.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 os.makedirs(OUT, exist_ok=True)
