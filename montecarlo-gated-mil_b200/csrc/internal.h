@@ -1,5 +1,6 @@
 // internal.h — host-side objects behind the opaque C-ABI handles and the kernel launchers.
 #pragma once
+#include <cstdlib>
 #include <vector>
 #include "common.cuh"
 #include "philox.cuh"
@@ -46,6 +47,21 @@ struct MaskSpec {
   int rounds;            // Philox rounds: 10 (default) or 7
   const uint32_t* inj_feat;   // [T][R][16] or null
   const uint32_t* inj_attn;   // [T][C][Rp/32] or null
+};
+
+// Programmatic dependent launch: the kernel may start (prologue, barrier / TMEM set-up, W loads) while
+// its stream predecessor drains; it must execute griddepcontrol.wait before touching anything the
+// predecessor wrote or still reads.  Hides ~2-4 us of launch latency per kernel in single-bag calls.
+struct PdlLaunch {
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool off = getenv("MCMIL_NO_PDL") != nullptr;     // A/B switch
+    cfg.attrs = attr; cfg.numAttrs = off ? 0 : 1;
+  }
 };
 
 // ---- launchers (each returns a cudaError_t and bumps *launches) ----

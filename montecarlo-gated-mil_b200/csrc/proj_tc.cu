@@ -192,6 +192,10 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * TMEM_SLOT);
 
+  // PDL: everything above and the W load below may overlap the tail of the previous kernel in the
+  // stream; the features (producers) and the logits / scores planes (epilogue; still read by the
+  // previous call's reduction kernels) may only be touched after griddepcontrol.wait.
+  grid_dep_launch();
   if (warp == MMA_WARP || warp == LOAD_WARP) {
     // ------------------------------------------------------------ TMA loader: this CTA's W rows, once
     if (warp == LOAD_WARP && lane == 0) {
@@ -268,6 +272,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       off[i] = (uint32_t)rowi[i] * 128u + (uint32_t)((chunk ^ (rowi[i] & 7)) << 4);
     }
     uint32_t tc = 0;                                  // samples processed so far by this pair
+    grid_dep_wait();
     for (long long u = u_begin; u < u_end;) {
       const int ti = (int)(u / P.T);
       const int t_begin = (int)(u - (long long)ti * P.T);
@@ -365,6 +370,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     const uint32_t tempty_leader = mapa(bar_addr(sbase, B_TEMPTY), 0);
     float* xch = reinterpret_cast<float*>(smem + SM_XCH);
     uint32_t tc = 0;
+    grid_dep_wait();
 #ifdef MCMIL_EXP_PRODUCER_ONLY
     for (long long u = u_end; u < u_end;) {
 #else
@@ -494,7 +500,11 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
     P.epi = w.epi[s];
     const KernelFn fn = dbg != nullptr ? debug_kernel
                                        : kernels[m.rounds == 7 ? 1 : 0][m.inj_feat != nullptr ? 1 : 0][P.n_out - 1];
-    fn<<<2 * n_pairs, TC_THREADS, SM_TOTAL, st>>>(P);
+    {
+      PdlLaunch L(dim3(2 * n_pairs), dim3(TC_THREADS), SM_TOTAL, st);
+      cudaError_t e = cudaLaunchKernelEx(&L.cfg, fn, P);
+      if (e != cudaSuccess) return e;
+    }
     if (launches) ++*launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -26,6 +26,8 @@ softmax_rows_kernel(const float* __restrict__ logits, const float* __restrict__ 
                     const int32_t* __restrict__ cu, int n_bags, int T, int C, int Rp,
                     float2* __restrict__ rowstat, float* __restrict__ Y) {
   __shared__ float red[2][ROW_THREADS / 32];
+  asm volatile("griddepcontrol.wait;" ::: "memory");         // logits / scores of the projection kernel
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int c = blockIdx.x % C;
   const int t = (blockIdx.x / C) % T;
   const int b = blockIdx.x / (C * T);
@@ -79,6 +81,8 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
                     float* __restrict__ A, float* __restrict__ attn_mean, float* __restrict__ attn_m2,
                     float* __restrict__ prob_mean, float* __restrict__ prob_m2) {
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  asm volatile("griddepcontrol.wait;" ::: "memory");         // rowstat / Y of softmax_rows_kernel
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if ((int)blockIdx.x < col_blocks) {
     __shared__ float s_mean[COL_TGROUPS][COL_LANES], s_m2[COL_TGROUPS][COL_LANES];
     const int c = blockIdx.y;
@@ -146,14 +150,26 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
 cudaError_t launch_reduce(const Plan& p, const float* logits, const float* scores, float2* rowstat,
                           float* Y, float* A, float* prob_mean, float* prob_m2, float* attn_mean,
                           float* attn_m2, cudaStream_t st, int* launches) {
-  softmax_rows_kernel<<<p.n_bags * p.T * p.C, ROW_THREADS, 0, st>>>(logits, scores, p.d_cu, p.n_bags, p.T, p.C,
-                                                                    p.Rp, rowstat, Y);
+  {
+    PdlLaunch L(dim3(p.n_bags * p.T * p.C), dim3(ROW_THREADS), 0, st);
+    const int32_t* cu = p.d_cu;
+    int n_bags = p.n_bags, T = p.T, C = p.C, Rp = p.Rp;
+    cudaError_t e = cudaLaunchKernelEx(&L.cfg, softmax_rows_kernel, logits, scores, cu, n_bags, T, C, Rp, rowstat, Y);
+    if (e != cudaSuccess) return e;
+  }
   if (launches) ++*launches;
   const int col_blocks = (p.R + COL_LANES - 1) / COL_LANES;
   const int bag_blocks = (p.n_bags + COL_TGROUPS - 1) / COL_TGROUPS;
-  welford_cols_kernel<<<dim3(col_blocks + bag_blocks, p.C), COL_THREADS, 0, st>>>(
-      logits, rowstat, p.d_row2bag, Y, p.n_bags, p.T, p.C, p.R, p.Rp, col_blocks, A, attn_mean, attn_m2,
-      prob_mean, prob_m2);
+  {
+    PdlLaunch L(dim3(col_blocks + bag_blocks, p.C), dim3(COL_THREADS), 0, st);
+    const float2* rs = rowstat;
+    const int32_t* r2b = p.d_row2bag;
+    const float* Yc = Y;
+    int n_bags = p.n_bags, T = p.T, C = p.C, R = p.R, Rp = p.Rp;
+    cudaError_t e = cudaLaunchKernelEx(&L.cfg, welford_cols_kernel, logits, rs, r2b, Yc, n_bags, T, C, R, Rp, col_blocks,
+                                       A, attn_mean, attn_m2, prob_mean, prob_m2);
+    if (e != cudaSuccess) return e;
+  }
   if (launches) ++*launches;
   return cudaGetLastError();
 }

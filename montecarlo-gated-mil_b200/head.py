@@ -220,7 +220,12 @@ def mc_head(weights: HeadWeights, H: torch.Tensor, T: int, seed: int = 0,
             if m.device != dev or m.element_size() != 4 or not m.is_contiguous():
                 raise ValueError("mc_head: injected masks must be contiguous 32-bit CUDA tensors")
 
-    with torch.cuda.device(dev):
+    # (no `with torch.cuda.device` context manager on the common path: host overhead matters for single-bag calls)
+    switch = torch.cuda.current_device() != dev.index
+    if switch:
+        prev = torch.cuda.current_device()
+        torch.cuda.set_device(dev)
+    try:
         Y = torch.empty((n_bags, T, C_), dtype=torch.float32, device=dev)
         A = torch.empty((T, C_, R), dtype=torch.float32, device=dev) if return_attention else None
         pm = torch.empty((n_bags, C_), dtype=torch.float32, device=dev)
@@ -235,6 +240,9 @@ def mc_head(weights: HeadWeights, H: torch.Tensor, T: int, seed: int = 0,
                                       _ptr(ws), ws.numel(), _stream_ptr(dev))
         _lib.check(code, "mcmil_head_forward")
         launches = int(lib.mcmil_last_launch_count())
+    finally:
+        if switch:
+            torch.cuda.set_device(prev)
     return MCHeadResult(Y, pm, pq, am, aq, A, T, cu, launches)
 
 
