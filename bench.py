@@ -290,11 +290,20 @@ def run_ours(args):
         n_chunks = (n_bags + chunk_bags - 1) // chunk_bags
         max_rows = max(int(cu[min(n_bags, (k + 1) * chunk_bags)] - cu[k * chunk_bags]) for k in range(n_chunks))
         dbuf = [torch.empty((max_rows, L), dtype=torch.float32, device=dev) for _ in range(2)]
-        outY = torch.empty((n_bags, T, C), dtype=torch.float32).pin_memory()
-        outP = torch.empty((2, n_bags, C), dtype=torch.float32).pin_memory()
-        outA = torch.empty((2, C, R), dtype=torch.float32).pin_memory()
+        # results land in flat pinned buffers (one per chunk): every D2H copy is a single contiguous
+        # cudaMemcpyAsync (a strided pinned destination makes torch stage + synchronise, which
+        # serialises the whole pipeline)
+        outY = [None] * n_chunks
+        outP = [None] * n_chunks
+        outA = [None] * n_chunks
+        for k in range(n_chunks):
+            b0, b1 = k * chunk_bags, min(n_bags, (k + 1) * chunk_bags)
+            rows = int(cu[b1] - cu[b0])
+            outY[k] = torch.empty((b1 - b0) * T * C, dtype=torch.float32).pin_memory()
+            outP[k] = torch.empty(2 * (b1 - b0) * C, dtype=torch.float32).pin_memory()
+            outA[k] = torch.empty(2 * C * rows, dtype=torch.float32).pin_memory()
         h2d = R * L * 4
-        d2h = outY.numel() * 4 + outP.numel() * 4 + outA.numel() * 4
+        d2h = sum(t.numel() for t in outY + outP + outA) * 4
 
         def e2e_step(i):
             for k in range(n_chunks):
@@ -307,11 +316,12 @@ def run_ours(args):
                     r = mm.mc_head(w, hb, T, seed=i, cu_seqlens=cu[b0:b1 + 1] - cu[b0],
                                    bag_ids=None if bag_ids is None else bag_ids[b0:b1], bag_offset=b0,
                                    t_offset=t_offset, philox_rounds=args.philox_rounds)
-                    outY[b0:b1].copy_(r.Y, non_blocking=True)
-                    outP[0, b0:b1].copy_(r.prob_mean, non_blocking=True)
-                    outP[1, b0:b1].copy_(r.prob_m2, non_blocking=True)
-                    outA[0, :, r0:r1].copy_(r.attn_mean, non_blocking=True)
-                    outA[1, :, r0:r1].copy_(r.attn_m2, non_blocking=True)
+                    nb_c, na_c = (b1 - b0) * C, C * (r1 - r0)
+                    outY[k].copy_(r.Y.view(-1), non_blocking=True)
+                    outP[k][:nb_c].copy_(r.prob_mean.view(-1), non_blocking=True)
+                    outP[k][nb_c:].copy_(r.prob_m2.view(-1), non_blocking=True)
+                    outA[k][:na_c].copy_(r.attn_mean.view(-1), non_blocking=True)
+                    outA[k][na_c:].copy_(r.attn_m2.view(-1), non_blocking=True)
             for s in streams:
                 s.synchronize()
 
