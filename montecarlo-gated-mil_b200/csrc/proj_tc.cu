@@ -14,9 +14,13 @@
 //   regs : each producer thread keeps ITS 16 chunks of the fp16 feature tile in registers for the
 //          whole work item (converted from the fp32 features once per item);
 //   TMEM : two accumulator buffers (double buffered across t).
-// Warp roles (14 warps with 2 producer teams): 0-3 epilogue (TMEM -> tanh/sigmoid/gate/w-dot -> logits),
+// Warp roles (16 warps with 2 producer teams): 0-3 epilogue (TMEM -> tanh/sigmoid/gate/w-dot -> logits),
 //   4-11 producers (Philox mask -> masked fp16 A slice, generic-proxy st.shared + proxy fence),
-//   12, 13 MMA issuers (even / odd samples; 12 owns the TMEM allocation, 13 first TMA-loads W).
+//   12-15 MMA issuers (sample tc is issued by warp 12 + tc % 4; 12 owns the TMEM allocation, 13 first
+//   TMA-loads W).  One issuer per SM sub-partition: issuing a sample's 64 tcgen05.mma costs its
+//   sub-partition ~25 % of a sample time, and with two issuers the two producer warps sharing their
+//   sub-partitions were the laggards every K-slice barrier waited for (profiles/r1_experiments.md).
+#include <cstdio>
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -29,28 +33,43 @@ using namespace ptx;
 constexpr int TEAMS = MCMIL_TEAMS;               // producer teams: team k fills the K-slices s = k (mod TEAMS)
 constexpr int TEAM_WARPS = 4;                    // warps per team (16 patch rows each)
 constexpr int TEAM_SLICES = NSLICE / TEAMS;      // slices per team and sample
+#ifndef MCMIL_MMA_WARPS
+#define MCMIL_MMA_WARPS 4   // MMA-issue warps, one per SM sub-partition of the leader CTA (see the role comment below)
+#endif
+constexpr int NMMA = MCMIL_MMA_WARPS;            // sample tc is issued by warp tc % NMMA into TMEM buffer tc & 1
+static_assert(NMMA == 2 || NMMA == 4, "MMA-issue warps: 2 or 4");
 constexpr int PRODUCER_WARP0 = 4, MMA_WARP = PRODUCER_WARP0 + TEAMS * TEAM_WARPS, LOAD_WARP = MMA_WARP + 1;
-constexpr int TC_THREADS = (LOAD_WARP + 1) * 32;
+constexpr int TC_THREADS = (MMA_WARP + NMMA) * 32;
 
 constexpr uint32_t SM_W = 0;
 constexpr uint32_t SM_RING = SM_W + NSLICE * SLICE_BYTES_W;        // 139264: 8 slots x 8 KB
 constexpr uint32_t SM_XCH = SM_RING + NSLICE * SLICE_BYTES_A;      // 204800: [2][64][4] floats
 constexpr uint32_t SM_BAR = SM_XCH + 2 * HALF_ROWS * MAXC * 4;     // 206848
-constexpr uint32_t SM_TOTAL = SM_BAR + 512;                        // 207360 <= 232448 (227 KB)
+constexpr uint32_t SM_TOTAL = SM_BAR + 1024;                       // 207872 <= 232448 (227 KB)
 
-// barrier slots (8 bytes each) inside SM_BAR.  The ring barriers exist twice, one set per sample
-// parity: samples are issued alternately by two MMA warps, and each warp must only ever see
-// consecutive phases of the barriers it waits on.
-enum : uint32_t {
-  B_FULL = 0,                      // [2][8] leader only: masked A slice of both CTAs is in smem (count 2 x TEAM_WARPS)
-  B_EMPTY = B_FULL + 2 * NSLICE,   // [2][8] per CTA: the MMAs reading the slot have retired     (count 1)
-  B_TFULL = B_EMPTY + 2 * NSLICE,  // [2] per CTA: accumulator buffer complete                   (count 1)
-  B_TEMPTY = B_TFULL + 2,          // [2] leader only: both CTAs' epilogues drained the buffer   (count 8)
-  B_WLOC = B_TEMPTY + 2,           // per CTA: W bulk copies landed                              (tx)
-  B_WREADY = B_WLOC + 1,           // leader only: both CTAs hold their W halves                 (count 2)
-  B_COUNT = B_WREADY + 1,
-  TMEM_SLOT = 48                   // uint32 at SM_BAR + 8*48
+// where the feature keep-masks come from
+enum : int {
+  MASK_PHILOX = 0,         // drawn in the kernel
+  MASK_INJECTED = 1,       // caller-provided bits (parity tests with the reference's own masks)
+  MASK_PHILOX_EXPORT = 2,  // drawn in the kernel and written to the mask cache (separate attention, first head)
+  MASK_CACHED = 3          // read back from the mask cache (separate attention, remaining heads): the SAME
+                           // H_drop feeds every head (model.py:281,297-298) without paying the RNG again
 };
+
+// barrier slots (8 bytes each) inside SM_BAR.  The ring barriers and the accumulator-empty barrier
+// exist once per MMA-issue warp: samples are issued round-robin by NMMA warps, and a parity wait is
+// only unambiguous for a waiter that sees consecutive phases of the barrier it waits on.
+enum : uint32_t {
+  B_FULL = 0,                         // [NMMA][8] leader only: masked A slice of both CTAs is in smem (count 2 x TEAM_WARPS)
+  B_EMPTY = B_FULL + NMMA * NSLICE,   // [NMMA][8] per CTA: the MMAs reading the slot have retired     (count 1)
+  B_TFULL = B_EMPTY + NMMA * NSLICE,  // [2] per CTA: accumulator buffer complete                      (count 1)
+  B_TEMPTY = B_TFULL + 2,             // [NMMA] leader only: both CTAs' epilogues drained the buffer   (count 8)
+  B_WLOC = B_TEMPTY + NMMA,           // per CTA: W bulk copies landed                                 (tx)
+  B_WREADY = B_WLOC + 1,              // leader only: both CTAs hold their W halves                    (count 2)
+  B_COUNT = B_WREADY + 1,
+  TMEM_SLOT = 100                     // uint32 at SM_BAR + 8*100
+};
+static_assert(B_COUNT <= TMEM_SLOT && 8 * (TMEM_SLOT + 1) <= 1024, "barrier area");
 
 // TMEM columns of one accumulator buffer (2x2 layout of the pair MMAs: lanes 0..63 hold the
 // columns fed by the leader CTA's W rows, lanes 64..127 those of the peer CTA's W rows):
@@ -67,6 +86,7 @@ struct ProjParams {
   float* scores;           // [T][C][Rp]
   const uint32_t* inj_feat;  // [T][R][16] or null
   const uint32_t* inj_attn;  // [T][C][Rp/32] or null
+  uint8_t* mask_cache;     // [T][R][8 chunks-in-slice][TEAMS][TEAM_SLICES] keep bytes, or null
   float* dbg;              // optional raw accumulator dump of each pair's first (tile, t)
   int n_tiles, T, C, R, Rp;
   int n_out;               // heads produced by this launch (shared: C, separate: 1)
@@ -79,6 +99,24 @@ struct ProjParams {
 };
 
 __device__ __forceinline__ uint32_t bar_addr(uint32_t sbase, uint32_t slot) { return sbase + SM_BAR + slot * 8; }
+
+// -DMCMIL_EXP_TRACE: the warps of one leader CTA time-stamp their barrier events for samples [64, 68)
+#ifdef MCMIL_EXP_TRACE
+#define TRACE_DECL long long trc[64]; for (int i_ = 0; i_ < 64; ++i_) trc[i_] = 0;
+#define TRACE(tcv, slot) do { if ((tcv) >= 64u && (tcv) < 68u) trc[((tcv) - 64u) * 16 + (slot)] = clock64() - k_t0; } while (0)
+#define TRACE_DUMP(role) do { if (pair == 3 && rank == 0 && lane == 0) { for (int a_ = 0; a_ < 64; ++a_) \
+    if (trc[a_] != 0) printf("TR %s %d %d %d %lld\n", role, warp, 64 + a_ / 16, a_ % 16, trc[a_]); } } while (0)
+#else
+#define TRACE_DECL
+#define TRACE(tcv, slot)
+#define TRACE_DUMP(role)
+#endif
+// -DMCMIL_EXP_WAITSTATS: every warp of the first cluster reports the cycles it spent in barrier waits
+#ifdef MCMIL_EXP_WAITSTATS
+#define WAIT_T(acc, bar, parity) do { const long long w0_ = clock64(); mbar_wait(bar, parity); acc += clock64() - w0_; } while (0)
+#else
+#define WAIT_T(acc, bar, parity) mbar_wait(bar, parity)
+#endif
 
 // keep -> all-ones half lanes.  r holds two 16-bit uniform lanes; an element is kept iff
 // (lane & 0x7fff) >= thr.  Positive fp16 bit patterns order like their integer values and the
@@ -101,6 +139,39 @@ __device__ __forceinline__ uint32_t keep_mask2_alu(uint32_t r, uint32_t thr2) {
 #ifndef MCMIL_MASK_RECIPE
 #define MCMIL_MASK_RECIPE 0      // 0: HSET2 for all four words, 1: ALU for all, 2: two and two
 #endif
+// keep byte (bit e <-> feature 8q+e) from the four all-ones/zero lane-pair masks; only byte 0 of the
+// result is meaningful
+__device__ __forceinline__ uint32_t keep_byte(const uint4& m) {
+  const uint32_t b = (m.x & 0x00020001u) | (m.y & 0x00080004u) | (m.z & 0x00200010u) | (m.w & 0x00800040u);
+  return b | (b >> 16);
+}
+// byte SI of w replaced by byte 0 of b
+template <int SI>
+__device__ __forceinline__ uint32_t insert_byte(uint32_t w, uint32_t b) {
+  constexpr uint32_t sel = SI == 0 ? 0x3214u : SI == 1 ? 0x3240u : SI == 2 ? 0x3410u : 0x4210u;
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(b), "n"(sel));
+  return r;
+}
+// Inverse of keep_byte without a table: byte SI of w -> the four lane-pair masks.  Two multiplies move
+// keep bit e to the top bit of byte e (of two words), PRMT's sign-replicate mode widens each top bit
+// to a 16-bit lane.  13 ALU-type instructions per chunk instead of a Philox call (~55).
+template <int SI>
+__device__ __forceinline__ uint4 expand_keep_byte(uint32_t w) {
+  uint32_t kb;
+  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(kb) : "r"(w), "n"(0x4440 | SI));
+  const uint32_t lo = (kb & 0x0Fu) * 0x10204080u;      // bit e -> bit 8e+7, e = 0..3
+  const uint32_t hi = (kb & 0xF0u) * 0x01020408u;      // bit e -> bit 8(e-4)+7, e = 4..7
+  uint4 m;
+  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(m.x) : "r"(lo));
+  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(m.y) : "r"(lo));
+  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(m.z) : "r"(hi));
+  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(m.w) : "r"(hi));
+  return m;
+}
+__device__ __forceinline__ uint4 keep_masks(const uint4& r, uint32_t thr2) {
+  return make_uint4(keep_mask2(r.x, thr2), keep_mask2(r.y, thr2), keep_mask2(r.z, thr2), keep_mask2(r.w, thr2));
+}
 __device__ __forceinline__ uint4 apply_keep(const uint4& h, const uint4& r, uint32_t thr2) {
   uint4 o;
 #if MCMIL_MASK_RECIPE == 0
@@ -158,14 +229,18 @@ __device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tbuf
   }
 }
 
-template <int NOUT, bool INJECT, bool DEBUG, int ROUNDS>
+template <int NOUT, int MASK, bool DEBUG, int ROUNDS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 proj_tc_kernel(const __grid_constant__ ProjParams P) {
+  constexpr bool INJECT = MASK == MASK_INJECTED;            // logit masks injected too
+  constexpr bool DRAW = MASK == MASK_PHILOX || MASK == MASK_PHILOX_EXPORT;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  long long wait_a = 0, wait_b = 0;          // MCMIL_EXP_WAITSTATS only
+  const long long k_t0 = clock64();
 
   // contiguous slice of the (tile, t) unit space owned by this pair
   const long long U = (long long)P.n_tiles * P.T;
@@ -173,11 +248,12 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 
   if ((sbase & 1023u) != 0) __trap();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2 * NSLICE; ++s) {
+    for (int s = 0; s < NMMA * NSLICE; ++s) {
       mbar_init(bar_addr(sbase, B_FULL + s), 2 * TEAM_WARPS);
       mbar_init(bar_addr(sbase, B_EMPTY + s), 1);
     }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_addr(sbase, B_TFULL + b), 1); mbar_init(bar_addr(sbase, B_TEMPTY + b), 8); }
+    for (int b = 0; b < 2; ++b) mbar_init(bar_addr(sbase, B_TFULL + b), 1);
+    for (int b = 0; b < NMMA; ++b) mbar_init(bar_addr(sbase, B_TEMPTY + b), 8);
     mbar_init(bar_addr(sbase, B_WLOC), 1);
     mbar_init(bar_addr(sbase, B_WREADY), 2);
     fence_mbar_init();
@@ -196,7 +272,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
   // stream; the features (producers) and the logits / scores planes (epilogue; still read by the
   // previous call's reduction kernels) may only be touched after griddepcontrol.wait.
   grid_dep_launch();
-  if (warp == MMA_WARP || warp == LOAD_WARP) {
+  if (warp >= MMA_WARP) {
     // ------------------------------------------------------------ TMA loader: this CTA's W rows, once
     if (warp == LOAD_WARP && lane == 0) {
       const uint32_t wloc = bar_addr(sbase, B_WLOC);
@@ -208,48 +284,67 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     }
     __syncwarp();
     // ------------------------------------------------------------ MMA issuers (leader CTA)
-    // Two issue warps, one per sample parity / accumulator buffer: a single warp shares its
-    // scheduler with three busy warps and needs ~500 cycles of issue latency per K-slice, twice the
-    // 272 cycles of tensor work it launches (profiles/r1).  Each warp runs its loop warp-uniformly
+    // NMMA issue warps take the samples round-robin: a single warp shares its scheduler with three
+    // busy warps and needs ~500 cycles of issue latency per K-slice, twice the 272 cycles of tensor
+    // work it launches (profiles/r1).  Each warp runs its loop warp-uniformly
     // (addresses / descriptors in uniform registers: a lane-0-only loop makes ptxas emit ELECT +
     // R2UR chains per MMA); one elected lane issues the tcgen05 ops.
     if (rank == 0) {
       constexpr uint32_t IDESC_A = umma_idesc_f16(128, 2 * W_ROWS_A);
       constexpr uint32_t IDESC_B = umma_idesc_f16(128, 2 * W_ROWS_B);
-      const uint32_t q = (uint32_t)(warp - MMA_WARP);          // sample parity and TMEM buffer of this warp
+      const uint32_t q = (uint32_t)(warp - MMA_WARP);          // this warp issues the samples tc = q (mod NMMA)
+      const uint32_t qb = q & 1u;                               // ... into TMEM accumulator buffer tc & 1
       mbar_wait(bar_addr(sbase, B_WREADY), 0);
       tc_fence_after();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t adesc0 = umma_desc_sw128(sbase + SM_RING);
       const uint64_t bdesc0 = umma_desc_sw128(sbase + SM_W);
-      const uint32_t da = tmem_u + q * TM_BUF_STRIDE + TM_A, db = tmem_u + q * TM_BUF_STRIDE + TM_B;
+      const uint32_t da = tmem_u + qb * TM_BUF_STRIDE + TM_A, db = tmem_u + qb * TM_BUF_STRIDE + TM_B;
       uint32_t j = 0;                                           // this warp's sample counter
+      TRACE_DECL
 #ifdef MCMIL_EXP_PRODUCER_ONLY
       if (true) goto exp_skip_mma;
 #endif
-      for (long long u = u_begin + q; u < u_end; u += 2, ++j) {
-        mbar_wait(bar_addr(sbase, B_TEMPTY + q), (j & 1) ^ 1);
+      for (long long u = u_begin + q; u < u_end; u += NMMA, ++j) {
+        TRACE(NMMA * j + q, 0);
+        // buffer tc & 1 was last used by sample tc - 2, whose epilogue arrives on TEMPTY[(tc - 2) % NMMA]:
+        // that is phase j of TEMPTY[q - 2] for q >= 2, phase j - 1 of TEMPTY[q + NMMA - 2] otherwise
+        WAIT_T(wait_b, bar_addr(sbase, B_TEMPTY + ((q + NMMA - 2) & (NMMA - 1))), q >= 2 ? (j & 1) : ((j & 1) ^ 1));
+        TRACE(NMMA * j + q, 1);
         tc_fence_after();
 #pragma unroll 1
         for (int s = 0; s < NSLICE; ++s) {
-          mbar_wait(bar_addr(sbase, B_FULL + q * NSLICE + s), j & 1);
+          WAIT_T(wait_a, bar_addr(sbase, B_FULL + q * NSLICE + s), j & 1);
           tc_fence_after();
           if (elect_one()) {
             // start-address field is (addr >> 4): advancing by bytes/16 stays inside the 14-bit field
             const uint64_t ad = adesc0 + (uint64_t)(s * (SLICE_BYTES_A >> 4));
             const uint64_t bd = bdesc0 + (uint64_t)(s * (SLICE_BYTES_W >> 4));
+#if defined(MCMIL_EXP_MMA_ORDER)
+#pragma unroll
+            for (int kk = 0; kk < KSLICE / 16; ++kk) umma_f16_cg2(da, ad + 2 * kk, bd + 2 * kk, IDESC_A, (s | kk) != 0);
+#pragma unroll
+            for (int kk = 0; kk < KSLICE / 16; ++kk)
+              umma_f16_cg2(db, ad + 2 * kk, bd + ((W_ROWS_A * 128) >> 4) + 2 * kk, IDESC_B, (s | kk) != 0);
+#elif defined(MCMIL_EXP_MMA_A_ONLY)
+#pragma unroll
+            for (int kk = 0; kk < KSLICE / 16; ++kk) umma_f16_cg2(da, ad + 2 * kk, bd + 2 * kk, IDESC_A, (s | kk) != 0);
+#else
 #pragma unroll
             for (int kk = 0; kk < KSLICE / 16; ++kk) {
               umma_f16_cg2(da, ad + 2 * kk, bd + 2 * kk, IDESC_A, (s | kk) != 0);
               umma_f16_cg2(db, ad + 2 * kk, bd + ((W_ROWS_A * 128) >> 4) + 2 * kk, IDESC_B, (s | kk) != 0);
             }
+#endif
             umma_commit_cg2_mc(bar_addr(sbase, B_EMPTY + q * NSLICE + s), 3);
           }
           __syncwarp();
+          TRACE(NMMA * j + q, 2 + s);
         }
-        if (elect_one()) umma_commit_cg2_mc(bar_addr(sbase, B_TFULL + q), 3);
+        if (elect_one()) umma_commit_cg2_mc(bar_addr(sbase, B_TFULL + qb), 3);
         __syncwarp();
       }
+      TRACE_DUMP("mma");
 #ifdef MCMIL_EXP_PRODUCER_ONLY
       exp_skip_mma:;
 #endif
@@ -272,6 +367,8 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       off[i] = (uint32_t)rowi[i] * 128u + (uint32_t)((chunk ^ (rowi[i] & 7)) << 4);
     }
     uint32_t tc = 0;                                  // samples processed so far by this pair
+    bool slot_free = false;                           // early probe result for the next ring slot
+    TRACE_DECL
     grid_dep_wait();
     for (long long u = u_begin; u < u_end;) {
       const int ti = (int)(u / P.T);
@@ -302,36 +399,90 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       }
       // Software pipeline: the Philox words of the NEXT slice are drawn next to the masking /
       // st.shared of the CURRENT one, so wide multiplies (fmaheavy pipe) and ALU / LSU work mix.
+      // The (sample, row) part of the counter (philox.cuh) is shared by the four slices of a sample.
       uint4 rnd[4];
-      if constexpr (!INJECT) {
+      uint32_t mt_lo = 0;
+      PhiloxRowPart rp[4];
+      if constexpr (DRAW) {
+        const uint32_t tg0 = (uint32_t)(P.t_offset + t_begin);
+        mt_lo = philox_sample_part(tg0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          rp[i] = philox_row_part(nrow[i], tg0, P.key);
+          rnd[i] = philox4x32_split<ROUNDS>((uint32_t)(team * 8 + chunk), bag, mt_lo, rp[i], P.key);
+        }
+      }
+      // mask cache (separate attention): one 64-byte record per (sample, packed row), byte
+      // [chunk][team][si] = keep bits of chunk (TEAMS*si+team)*8+chunk; a thread owns one 32-bit word
+      // of it per row slot and sample.
+      static_assert(!(MASK == MASK_PHILOX_EXPORT || MASK == MASK_CACHED) || (TEAMS == 2 && TEAM_SLICES == 4),
+                    "mask cache layout assumes two producer teams");
+      size_t crow[4];
+      bool rvalid[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        rvalid[i] = (int)rank * HALF_ROWS + rowi[i] < td.nrows;
+        crow[i] = (size_t)(td.row0 + (int)rank * HALF_ROWS + rowi[i]) * 64 + chunk * 8 + team * 4;
+      }
+      uint32_t cw[4] = {0u, 0u, 0u, 0u};
+      if constexpr (MASK == MASK_CACHED) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          rnd[i] = philox4x32<ROUNDS>((uint32_t)(team * 8 + chunk), nrow[i], (uint32_t)(P.t_offset + t_begin), bag, P.key);
+          if (rvalid[i]) cw[i] = __ldg(reinterpret_cast<const uint32_t*>(P.mask_cache + (size_t)t_begin * P.R * 64 + crow[i]));
       }
 #pragma unroll 1
       for (int t = t_begin; t < t_end; ++t, ++tc) {
         const uint32_t tg = (uint32_t)(P.t_offset + t);
         // slot s was last read by the MMAs of sample tc-1, issued by warp (tc-1)&1 as its ((tc-1)>>1)-th
-        const uint32_t empty_set = ((tc + 1) & 1) * NSLICE, empty_parity = ((tc - 1) >> 1) & 1;
-        const uint32_t full_set = (tc & 1) * NSLICE;
+        constexpr uint32_t LOGM = NMMA == 4 ? 2 : 1;
+        const uint32_t empty_set = ((tc - 1) & (NMMA - 1)) * NSLICE, empty_parity = ((tc - 1) >> LOGM) & 1;
+        const uint32_t full_set = (tc & (NMMA - 1)) * NSLICE;
+        uint32_t cnext[4] = {0u, 0u, 0u, 0u};
+        if constexpr (MASK == MASK_CACHED) {                   // prefetch the next sample's keep bytes
+          if (t + 1 < t_end) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (rvalid[i]) cnext[i] = __ldg(reinterpret_cast<const uint32_t*>(P.mask_cache + (size_t)(t + 1) * P.R * 64 + crow[i]));
+          }
+        }
 #pragma unroll
         for (int si = 0; si < TEAM_SLICES; ++si) {
           const int s = TEAMS * si + team;
 #ifndef MCMIL_EXP_PRODUCER_ONLY
-          if (tc > 0) mbar_wait(bar_addr(sbase, B_EMPTY + empty_set + s), empty_parity);
+          TRACE(tc, 4 * si);
+#ifndef MCMIL_NO_EARLY_PROBE
+          if (tc > 0 && !slot_free) WAIT_T(wait_a, bar_addr(sbase, B_EMPTY + empty_set + s), empty_parity);
+#else
+          if (tc > 0) WAIT_T(wait_a, bar_addr(sbase, B_EMPTY + empty_set + s), empty_parity);
+#endif
+          TRACE(tc, 4 * si + 1);
+#endif
+#ifdef MCMIL_EXP_MMA_ONLY       // experiment: no producer work at all, the MMA / epilogue chain runs flat out
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(full_leader + (full_set + s) * 8);
+          continue;
 #endif
           uint4 nxt[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint4 h = hreg[si][i];
             uint4 o;
-            if constexpr (!INJECT) {
+            if constexpr (MASK == MASK_PHILOX) {
 #ifdef MCMIL_EXP_NO_MASK
               o = h;
               asm volatile("" :: "r"(rnd[i].x), "r"(rnd[i].y), "r"(rnd[i].z), "r"(rnd[i].w));
 #else
               o = apply_keep(h, rnd[i], thr2);
 #endif
+            } else if constexpr (MASK == MASK_PHILOX_EXPORT) {
+              const uint4 m = keep_masks(rnd[i], thr2);
+              o = make_uint4(h.x & m.x, h.y & m.y, h.z & m.z, h.w & m.w);
+              cw[i] = si == 0 ? insert_byte<0>(cw[i], keep_byte(m)) : si == 1 ? insert_byte<1>(cw[i], keep_byte(m))
+                    : si == 2 ? insert_byte<2>(cw[i], keep_byte(m)) : insert_byte<3>(cw[i], keep_byte(m));
+            } else if constexpr (MASK == MASK_CACHED) {
+              const uint4 m = si == 0 ? expand_keep_byte<0>(cw[i]) : si == 1 ? expand_keep_byte<1>(cw[i])
+                            : si == 2 ? expand_keep_byte<2>(cw[i]) : expand_keep_byte<3>(cw[i]);
+              o = make_uint4(h.x & m.x, h.y & m.y, h.z & m.z, h.w & m.w);
             } else {
               const int trow = (int)rank * HALF_ROWS + rowi[i];
               uint32_t bits = 0;
@@ -344,24 +495,52 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
             }
             *reinterpret_cast<uint4*>(smem + SM_RING + s * SLICE_BYTES_A + off[i]) = o;
           }
-          if constexpr (!INJECT) {
+#if !defined(MCMIL_NO_EARLY_PROBE) && !defined(MCMIL_EXP_PRODUCER_ONLY)
+          // Probe the barrier of the NEXT slot now: the answer (an ~200-cycle round trip through the
+          // barrier unit while the tensor core streams operands out of smem) arrives during the Philox
+          // block below; the blocking wait above is only entered when the slot is really still in use.
+          {
+            const bool last = si == TEAM_SLICES - 1;
+            const uint32_t nset = last ? full_set : empty_set;                       // empty_set of sample tc+1 == full_set of tc
+            const uint32_t npar = last ? ((tc >> LOGM) & 1) : empty_parity;
+            const int ns = last ? team : s + TEAMS;
+            slot_free = (last || tc > 0) && mbar_test_wait(bar_addr(sbase, B_EMPTY + nset + ns), npar);
+          }
+#endif
+          if constexpr (DRAW) {
             // next slice of this team: (s + TEAMS, t), or (team, t + 1) after the last one of the sample
             const uint32_t q_next = (uint32_t)((si < TEAM_SLICES - 1 ? s + TEAMS : team) * 8 + chunk);
-            const uint32_t t_next = si < TEAM_SLICES - 1 ? tg : tg + 1u;
+            if (si == TEAM_SLICES - 1) {
+              mt_lo = philox_sample_part(tg + 1u);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) nxt[i] = philox4x32<ROUNDS>(q_next, nrow[i], t_next, bag, P.key);
+              for (int i = 0; i < 4; ++i) rp[i] = philox_row_part(nrow[i], tg + 1u, P.key);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) nxt[i] = philox4x32_split<ROUNDS>(q_next, bag, mt_lo, rp[i], P.key);
           }
+          TRACE(tc, 4 * si + 2);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(full_leader + (full_set + s) * 8);
-          if constexpr (!INJECT) {
+          TRACE(tc, 4 * si + 3);
+          if constexpr (DRAW) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) rnd[i] = nxt[i];
           }
         }
+        if constexpr (MASK == MASK_PHILOX_EXPORT) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (rvalid[i]) *reinterpret_cast<uint32_t*>(P.mask_cache + (size_t)t * P.R * 64 + crow[i]) = cw[i];
+        }
+        if constexpr (MASK == MASK_CACHED) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cw[i] = cnext[i];
+        }
       }
       u = u_next < u_end ? u_next : u_end;
     }
+    TRACE_DUMP("prod");
   } else {
     // ------------------------------------------------------------ epilogue warps 0..3
     const int half = warp >> 1;                    // TMEM lanes 64..127: the peer CTA's W rows
@@ -370,6 +549,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     const uint32_t tempty_leader = mapa(bar_addr(sbase, B_TEMPTY), 0);
     float* xch = reinterpret_cast<float*>(smem + SM_XCH);
     uint32_t tc = 0;
+    TRACE_DECL
     grid_dep_wait();
 #ifdef MCMIL_EXP_PRODUCER_ONLY
     for (long long u = u_end; u < u_end;) {
@@ -386,7 +566,9 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       const int g = td.row0 + trow;
       for (int t = t_begin; t < t_end; ++t, ++tc) {
         const uint32_t buf = tc & 1;
-        mbar_wait(bar_addr(sbase, B_TFULL + buf), (tc >> 1) & 1);
+        TRACE(tc, 0);
+        WAIT_T(wait_a, bar_addr(sbase, B_TFULL + buf), (tc >> 1) & 1);
+        TRACE(tc, 1);
         tc_fence_after();
         float acc[MAXC] = {0.f, 0.f, 0.f, 0.f};
         float* dbg_row = nullptr;
@@ -407,7 +589,8 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tempty_leader + buf * 8);
+        if (lane == 0) mbar_arrive_cluster(tempty_leader + (tc & (NMMA - 1)) * 8);
+        TRACE(tc, 2);
         // combine the two hidden-unit halves of each patch row
         float* x = xch + ((tc & 1) * HALF_ROWS + r) * MAXC;
         if (half == 1) {
@@ -436,8 +619,15 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       }
       u = u_next < u_end ? u_next : u_end;
     }
+    TRACE_DUMP("epi");
   }
 
+#ifdef MCMIL_EXP_WAITSTATS
+  if (pair == 3 && lane == 0)
+    printf("WS rank %u warp %2d total %lld wait_a %lld wait_b %lld\n", rank, warp, clock64() - k_t0, wait_a, wait_b);
+#else
+  (void)wait_a; (void)wait_b; (void)k_t0;
+#endif
   // ---------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
@@ -449,24 +639,30 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 }
 
 cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const float* H,
-                           float* logits, float* scores, float* dbg, cudaStream_t st, int* launches) {
+                           float* logits, float* scores, uint8_t* mask_cache, float* dbg, cudaStream_t st,
+                           int* launches) {
   using KernelFn = void (*)(ProjParams);
-  // [rounds 10 / 7][in-kernel Philox / injected masks][heads per launch]
-  static const KernelFn kernels[2][2][4] = {
-      {{proj_tc_kernel<1, false, false, 10>, proj_tc_kernel<2, false, false, 10>, proj_tc_kernel<3, false, false, 10>,
-        proj_tc_kernel<4, false, false, 10>},
-       {proj_tc_kernel<1, true, false, 10>, proj_tc_kernel<2, true, false, 10>, proj_tc_kernel<3, true, false, 10>,
-        proj_tc_kernel<4, true, false, 10>}},
-      {{proj_tc_kernel<1, false, false, 7>, proj_tc_kernel<2, false, false, 7>, proj_tc_kernel<3, false, false, 7>,
-        proj_tc_kernel<4, false, false, 7>},
-       {proj_tc_kernel<1, true, false, 10>, proj_tc_kernel<2, true, false, 10>, proj_tc_kernel<3, true, false, 10>,
-        proj_tc_kernel<4, true, false, 10>}}};
-  static const KernelFn debug_kernel = proj_tc_kernel<2, false, true, 10>;   // raw-accumulator dump (tests only)
+  // [rounds 10 / 7][mask source][heads per launch]; export / cached exist for one head per launch only
+  static const KernelFn kernels[2][4][4] = {
+      {{proj_tc_kernel<1, MASK_PHILOX, false, 10>, proj_tc_kernel<2, MASK_PHILOX, false, 10>,
+        proj_tc_kernel<3, MASK_PHILOX, false, 10>, proj_tc_kernel<4, MASK_PHILOX, false, 10>},
+       {proj_tc_kernel<1, MASK_INJECTED, false, 10>, proj_tc_kernel<2, MASK_INJECTED, false, 10>,
+        proj_tc_kernel<3, MASK_INJECTED, false, 10>, proj_tc_kernel<4, MASK_INJECTED, false, 10>},
+       {proj_tc_kernel<1, MASK_PHILOX_EXPORT, false, 10>, nullptr, nullptr, nullptr},
+       {proj_tc_kernel<1, MASK_CACHED, false, 10>, nullptr, nullptr, nullptr}},
+      {{proj_tc_kernel<1, MASK_PHILOX, false, 7>, proj_tc_kernel<2, MASK_PHILOX, false, 7>,
+        proj_tc_kernel<3, MASK_PHILOX, false, 7>, proj_tc_kernel<4, MASK_PHILOX, false, 7>},
+       {proj_tc_kernel<1, MASK_INJECTED, false, 10>, proj_tc_kernel<2, MASK_INJECTED, false, 10>,
+        proj_tc_kernel<3, MASK_INJECTED, false, 10>, proj_tc_kernel<4, MASK_INJECTED, false, 10>},
+       {proj_tc_kernel<1, MASK_PHILOX_EXPORT, false, 7>, nullptr, nullptr, nullptr},
+       {proj_tc_kernel<1, MASK_CACHED, false, 7>, nullptr, nullptr, nullptr}}};
+  static const KernelFn debug_kernel = proj_tc_kernel<2, MASK_PHILOX, true, 10>;   // raw-accumulator dump (tests only)
   static bool attr_set = false;
   if (!attr_set) {
     for (int r = 0; r < 2; ++r)
-      for (int a = 0; a < 2; ++a)
+      for (int a = 0; a < 4; ++a)
         for (int b = 0; b < 4; ++b) {
+          if (kernels[r][a][b] == nullptr) continue;
           cudaError_t e = cudaFuncSetAttribute(kernels[r][a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
           if (e != cudaSuccess) return e;
         }
@@ -489,6 +685,7 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
     P.tiles = p.d_tiles;
     P.logits = logits; P.scores = scores;
     P.inj_feat = m.inj_feat; P.inj_attn = m.inj_attn;
+    P.mask_cache = mask_cache;
     P.dbg = dbg;
     P.n_tiles = p.n_tiles; P.T = p.T; P.C = p.C; P.R = p.R; P.Rp = p.Rp;
     P.n_out = w.shared ? w.C : 1;
@@ -498,8 +695,10 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
     P.sf = m.sf; P.hsf = 0.5f * m.sf; P.sa = m.sa;
     P.key = m.key;
     P.epi = w.epi[s];
-    const KernelFn fn = dbg != nullptr ? debug_kernel
-                                       : kernels[m.rounds == 7 ? 1 : 0][m.inj_feat != nullptr ? 1 : 0][P.n_out - 1];
+    // separate attention: the first head draws the masks and exports them, the others read them back
+    int mask_mode = m.inj_feat != nullptr ? MASK_INJECTED : MASK_PHILOX;
+    if (mask_mode == MASK_PHILOX && w.S > 1 && mask_cache != nullptr) mask_mode = s == 0 ? MASK_PHILOX_EXPORT : MASK_CACHED;
+    const KernelFn fn = dbg != nullptr ? debug_kernel : kernels[m.rounds == 7 ? 1 : 0][mask_mode][P.n_out - 1];
     {
       PdlLaunch L(dim3(2 * n_pairs), dim3(TC_THREADS), SM_TOTAL, st);
       cudaError_t e = cudaLaunchKernelEx(&L.cfg, fn, P);

@@ -60,6 +60,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)MCMIL_WAIT_HINT_NS) : "memory");
   return ok != 0;
 }
+// non-blocking probe: lets a warp ask early and hide the ~200-cycle barrier round trip behind other work
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 // A protocol bug must not hang the GPU: the spin is bounded and traps (launch failure) instead.
 // -DMCMIL_UNBOUNDED_WAITS drops the counter (~1 % faster).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
