@@ -136,9 +136,6 @@ __device__ __forceinline__ uint32_t keep_mask2_alu(uint32_t r, uint32_t thr2) {
   asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(m) : "r"(b));
   return m;
 }
-#ifndef MCMIL_MASK_RECIPE
-#define MCMIL_MASK_RECIPE 0      // 0: HSET2 for all four words, 1: ALU for all, 2: two and two
-#endif
 // keep byte (bit e <-> feature 8q+e) from the four all-ones/zero lane-pair masks; only byte 0 of the
 // result is meaningful
 __device__ __forceinline__ uint32_t keep_byte(const uint4& m) {
@@ -155,7 +152,7 @@ __device__ __forceinline__ uint32_t insert_byte(uint32_t w, uint32_t b) {
 }
 // Inverse of keep_byte without a table: byte SI of w -> the four lane-pair masks.  Two multiplies move
 // keep bit e to the top bit of byte e (of two words), PRMT's sign-replicate mode widens each top bit
-// to a 16-bit lane.  13 ALU-type instructions per chunk instead of a Philox call (~55).
+// to a 16-bit lane.  13 ALU-type instructions per chunk instead of a Philox call.
 template <int SI>
 __device__ __forceinline__ uint4 expand_keep_byte(uint32_t w) {
   uint32_t kb;
@@ -169,22 +166,14 @@ __device__ __forceinline__ uint4 expand_keep_byte(uint32_t w) {
   asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(m.w) : "r"(hi));
   return m;
 }
-__device__ __forceinline__ uint4 keep_masks(const uint4& r, uint32_t thr2) {
-  return make_uint4(keep_mask2(r.x, thr2), keep_mask2(r.y, thr2), keep_mask2(r.z, thr2), keep_mask2(r.w, thr2));
-}
-__device__ __forceinline__ uint4 apply_keep(const uint4& h, const uint4& r, uint32_t thr2) {
-  uint4 o;
-#if MCMIL_MASK_RECIPE == 0
-  o.x = h.x & keep_mask2(r.x, thr2); o.y = h.y & keep_mask2(r.y, thr2);
-  o.z = h.z & keep_mask2(r.z, thr2); o.w = h.w & keep_mask2(r.w, thr2);
-#elif MCMIL_MASK_RECIPE == 1
-  o.x = h.x & keep_mask2_alu(r.x, thr2); o.y = h.y & keep_mask2_alu(r.y, thr2);
-  o.z = h.z & keep_mask2_alu(r.z, thr2); o.w = h.w & keep_mask2_alu(r.w, thr2);
-#else
-  o.x = h.x & keep_mask2(r.x, thr2); o.y = h.y & keep_mask2_alu(r.y, thr2);
-  o.z = h.z & keep_mask2(r.z, thr2); o.w = h.w & keep_mask2_alu(r.w, thr2);
-#endif
-  return o;
+// The four lane-pair keep masks of one (row, chunk) from its 8 primary bytes (wa: features 0..3,
+// wb: 4..7) and the refinement byte `si` of rw (philox.cuh): each 16-bit lane is built as
+// (primary << 8) | refinement by one PRMT and compared by one HSET2.
+__device__ __forceinline__ uint4 keep_masks(uint32_t wa, uint32_t wb, uint32_t rw, int si, uint32_t thr2) {
+  const uint32_t r = 4u + (uint32_t)si;
+  const uint32_t s01 = 0x1000u | (r << 8) | r, s23 = 0x3020u | (r << 8) | r;     // [R, b0, R, b1], [R, b2, R, b3]
+  return make_uint4(keep_mask2(__byte_perm(wa, rw, s01), thr2), keep_mask2(__byte_perm(wa, rw, s23), thr2),
+                    keep_mask2(__byte_perm(wb, rw, s01), thr2), keep_mask2(__byte_perm(wb, rw, s23), thr2));
 }
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -399,18 +388,17 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       }
       // Software pipeline: the Philox words of the NEXT slice are drawn next to the masking /
       // st.shared of the CURRENT one, so wide multiplies (fmaheavy pipe) and ALU / LSU work mix.
-      // The (sample, row) part of the counter (philox.cuh) is shared by the four slices of a sample.
-      uint4 rnd[4];
-      uint32_t mt_lo = 0;
-      PhiloxRowPart rp[4];
+      // Mask convention (philox.cuh): one primary call serves this thread's chunk of two rows (row
+      // slots 0|1 and 2|3 differ in patch bit 2), one refinement call per sample serves its 16
+      // (row slot, slice) chunks: 9 calls per sample and thread.
+      static_assert(!DRAW || (TEAMS == 2 && TEAM_SLICES == 4), "refinement-byte indexing assumes two producer teams");
+      uint4 rnd[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};   // primary bytes: [0] row slots 0 (x,y) | 1 (z,w), [1] slots 2 | 3
+      uint4 ref = make_uint4(0, 0, 0, 0);                                // word i: row slot i, byte si: this team's si-th slice
       if constexpr (DRAW) {
         const uint32_t tg0 = (uint32_t)(P.t_offset + t_begin);
-        mt_lo = philox_sample_part(tg0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          rp[i] = philox_row_part(nrow[i], tg0, P.key);
-          rnd[i] = philox4x32_split<ROUNDS>((uint32_t)(team * 8 + chunk), bag, mt_lo, rp[i], P.key);
-        }
+        ref = philox4x32<ROUNDS>(REF_CHUNK_BASE + (uint32_t)(team * 8 + chunk), nrow[0], tg0, bag, P.key);
+        rnd[0] = philox4x32<ROUNDS>((uint32_t)(team * 8 + chunk), nrow[0], tg0, bag, P.key);
+        rnd[1] = philox4x32<ROUNDS>((uint32_t)(team * 8 + chunk), nrow[2], tg0, bag, P.key);
       }
       // mask cache (separate attention): one 64-byte record per (sample, packed row), byte
       // [chunk][team][si] = keep bits of chunk (TEAMS*si+team)*8+chunk; a thread owns one 32-bit word
@@ -462,38 +450,38 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
           if (lane == 0) mbar_arrive_cluster(full_leader + (full_set + s) * 8);
           continue;
 #endif
-          uint4 nxt[4];
+          uint4 nxt[2], ref_nxt = ref;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint4 h = hreg[si][i];
-            uint4 o;
-            if constexpr (MASK == MASK_PHILOX) {
+            uint4 m;                                             // lane-pair keep masks of this (row slot, chunk)
+            if constexpr (DRAW) {
+              const uint32_t wa = (i & 1) ? rnd[i >> 1].z : rnd[i >> 1].x, wb = (i & 1) ? rnd[i >> 1].w : rnd[i >> 1].y;
+              const uint32_t rw = i == 0 ? ref.x : i == 1 ? ref.y : i == 2 ? ref.z : ref.w;
 #ifdef MCMIL_EXP_NO_MASK
-              o = h;
-              asm volatile("" :: "r"(rnd[i].x), "r"(rnd[i].y), "r"(rnd[i].z), "r"(rnd[i].w));
+              m = make_uint4(~0u, ~0u, ~0u, ~0u);
+              asm volatile("" :: "r"(wa), "r"(wb), "r"(rw));
 #else
-              o = apply_keep(h, rnd[i], thr2);
+              m = keep_masks(wa, wb, rw, si, thr2);
 #endif
-            } else if constexpr (MASK == MASK_PHILOX_EXPORT) {
-              const uint4 m = keep_masks(rnd[i], thr2);
-              o = make_uint4(h.x & m.x, h.y & m.y, h.z & m.z, h.w & m.w);
-              cw[i] = si == 0 ? insert_byte<0>(cw[i], keep_byte(m)) : si == 1 ? insert_byte<1>(cw[i], keep_byte(m))
-                    : si == 2 ? insert_byte<2>(cw[i], keep_byte(m)) : insert_byte<3>(cw[i], keep_byte(m));
+              if constexpr (MASK == MASK_PHILOX_EXPORT)
+                cw[i] = si == 0 ? insert_byte<0>(cw[i], keep_byte(m)) : si == 1 ? insert_byte<1>(cw[i], keep_byte(m))
+                      : si == 2 ? insert_byte<2>(cw[i], keep_byte(m)) : insert_byte<3>(cw[i], keep_byte(m));
             } else if constexpr (MASK == MASK_CACHED) {
-              const uint4 m = si == 0 ? expand_keep_byte<0>(cw[i]) : si == 1 ? expand_keep_byte<1>(cw[i])
-                            : si == 2 ? expand_keep_byte<2>(cw[i]) : expand_keep_byte<3>(cw[i]);
-              o = make_uint4(h.x & m.x, h.y & m.y, h.z & m.z, h.w & m.w);
+              m = si == 0 ? expand_keep_byte<0>(cw[i]) : si == 1 ? expand_keep_byte<1>(cw[i])
+                : si == 2 ? expand_keep_byte<2>(cw[i]) : expand_keep_byte<3>(cw[i]);
             } else {
               const int trow = (int)rank * HALF_ROWS + rowi[i];
               uint32_t bits = 0;
               if (trow < td.nrows)
                 bits = reinterpret_cast<const uint8_t*>(P.inj_feat)[((size_t)t * P.R + td.row0 + trow) * 64 + s * 8 + chunk];
-              o.x = h.x & ((bits & 1u ? 0x0000FFFFu : 0u) | (bits & 2u ? 0xFFFF0000u : 0u));
-              o.y = h.y & ((bits & 4u ? 0x0000FFFFu : 0u) | (bits & 8u ? 0xFFFF0000u : 0u));
-              o.z = h.z & ((bits & 16u ? 0x0000FFFFu : 0u) | (bits & 32u ? 0xFFFF0000u : 0u));
-              o.w = h.w & ((bits & 64u ? 0x0000FFFFu : 0u) | (bits & 128u ? 0xFFFF0000u : 0u));
+              m.x = (bits & 1u ? 0x0000FFFFu : 0u) | (bits & 2u ? 0xFFFF0000u : 0u);
+              m.y = (bits & 4u ? 0x0000FFFFu : 0u) | (bits & 8u ? 0xFFFF0000u : 0u);
+              m.z = (bits & 16u ? 0x0000FFFFu : 0u) | (bits & 32u ? 0xFFFF0000u : 0u);
+              m.w = (bits & 64u ? 0x0000FFFFu : 0u) | (bits & 128u ? 0xFFFF0000u : 0u);
             }
-            *reinterpret_cast<uint4*>(smem + SM_RING + s * SLICE_BYTES_A + off[i]) = o;
+            *reinterpret_cast<uint4*>(smem + SM_RING + s * SLICE_BYTES_A + off[i]) =
+                make_uint4(h.x & m.x, h.y & m.y, h.z & m.z, h.w & m.w);
           }
 #if !defined(MCMIL_NO_EARLY_PROBE) && !defined(MCMIL_EXP_PRODUCER_ONLY)
           // Probe the barrier of the NEXT slot now: the answer (an ~200-cycle round trip through the
@@ -510,23 +498,18 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
           if constexpr (DRAW) {
             // next slice of this team: (s + TEAMS, t), or (team, t + 1) after the last one of the sample
             const uint32_t q_next = (uint32_t)((si < TEAM_SLICES - 1 ? s + TEAMS : team) * 8 + chunk);
-            if (si == TEAM_SLICES - 1) {
-              mt_lo = philox_sample_part(tg + 1u);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) rp[i] = philox_row_part(nrow[i], tg + 1u, P.key);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) nxt[i] = philox4x32_split<ROUNDS>(q_next, bag, mt_lo, rp[i], P.key);
+            const uint32_t t_next = si < TEAM_SLICES - 1 ? tg : tg + 1u;
+            nxt[0] = philox4x32<ROUNDS>(q_next, nrow[0], t_next, bag, P.key);
+            nxt[1] = philox4x32<ROUNDS>(q_next, nrow[2], t_next, bag, P.key);
+            if (si == TEAM_SLICES - 1)
+              ref_nxt = philox4x32<ROUNDS>(REF_CHUNK_BASE + (uint32_t)(team * 8 + chunk), nrow[0], t_next, bag, P.key);
           }
           TRACE(tc, 4 * si + 2);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(full_leader + (full_set + s) * 8);
           TRACE(tc, 4 * si + 3);
-          if constexpr (DRAW) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rnd[i] = nxt[i];
-          }
+          if constexpr (DRAW) { rnd[0] = nxt[0]; rnd[1] = nxt[1]; ref = ref_nxt; }
         }
         if constexpr (MASK == MASK_PHILOX_EXPORT) {
 #pragma unroll

@@ -15,10 +15,13 @@ Philox4x32-10 follows Salmon et al., "Parallel random numbers: as easy as
 Mask convention (mirrored by `csrc/philox.cuh`):
 
 * key  = (seed & 0xffffffff, seed >> 32)
-* feature mask of bag `b`, MC sample `t` (global index), patch `n`, feature
-  chunk `q = l // 8` (64 chunks of 8 features):
-      ctr = (q, n, t, b);   out = philox(ctr, key)            # 4 x u32
-      element e = l % 8 uses the 16-bit lane  (out[e >> 1] >> (16 * (e & 1))) & 0xffff
+* feature mask of bag `b`, MC sample `t` (global index), patch `n`, feature `l` (chunk `q = l // 8`,
+  K-slice `s = l // 64`): a 15-bit lane built from a *primary* byte P and a *refinement* byte R,
+      P = byte 8*((n>>2)&1) + l%8          of philox((q, n & ~4, t, b), key)                    # 16 bytes, LE
+      R = byte 4*((n>>2)&3) + (s>>1)       of philox((128 + (s&1)*8 + q%8, n & ~12, t, b), key)
+      lane = (P << 8) | R
+  (one primary call serves 8 features of the two rows n, n^4; R is shared by the 8 features of a
+  (row, chunk) and only matters when the 7 primary bits equal the top bits of the threshold)
 * logit mask of (b, t, n), head c:
       ctr = (64 + c // 4, n, t, b);  lane = out[c % 4] & 0xffff
 * keep  <=>  (lane & 0x7fff) >= thr,   thr = floor(p * 32768 + 0.5) in float32   (15-bit Bernoulli,
@@ -34,7 +37,8 @@ PHILOX_W0 = 0x9E3779B9
 PHILOX_W1 = 0xBB67AE85
 MASK32 = np.uint64(0xFFFFFFFF)
 
-ATTN_CHUNK_BASE = 64  # ctr[0] values >= 64 are the logit-dropout slots
+ATTN_CHUNK_BASE = 64  # ctr[0] in [64, 128): logit-dropout slots
+REF_CHUNK_BASE = 128  # ctr[0] in [128, 144): refinement bytes of the feature masks
 
 
 def philox4x32(ctr, key, rounds: int = 10):
@@ -68,20 +72,34 @@ def _key(seed: int):
     return seed & 0xFFFFFFFF, seed >> 32
 
 
+def _bytes_le(words):
+    """4 uint32 arrays [...]: -> uint32 array [..., 16] of their little-endian bytes."""
+    out = np.empty(words[0].shape + (16,), dtype=np.uint32)
+    for w in range(4):
+        for k in range(4):
+            out[..., 4 * w + k] = (words[w] >> np.uint32(8 * k)) & np.uint32(0xFF)
+    return out
+
+
 def feature_keep(seed: int, bag: int, t0: int, T: int, N: int, p: float, L: int = 512, rounds: int = 10) -> np.ndarray:
     """keep[t, n, l] in {0,1} (uint8) for t in [t0, t0+T), n in [0, N)."""
-    assert L % 8 == 0
+    assert L % 64 == 0
     thr = drop_threshold(p)
     Q = L // 8
     keep = np.empty((T, N, L), dtype=np.uint8)
     q = np.arange(Q, dtype=np.uint32)[None, :]
     n = np.arange(N, dtype=np.uint32)[:, None]
+    refq = np.uint32(REF_CHUNK_BASE) + ((q >> np.uint32(3)) & np.uint32(1)) * np.uint32(8) + (q & np.uint32(7))
+    half = ((n >> np.uint32(2)) & np.uint32(1)).astype(np.int64)              # which 8 bytes of the primary call
+    ridx = (4 * ((n >> np.uint32(2)) & np.uint32(3)) + (q >> np.uint32(4))).astype(np.int64)   # [N, Q] refinement byte index
+    e = np.arange(8, dtype=np.int64)[None, None, :]
     for i in range(T):
-        out = philox4x32((q, n, np.uint32(t0 + i), np.uint32(bag)), _key(seed), rounds)
-        lanes = np.empty((N, Q, 8), dtype=np.uint32)
-        for w in range(4):
-            lanes[:, :, 2 * w] = out[w] & np.uint32(0xFFFF)
-            lanes[:, :, 2 * w + 1] = out[w] >> np.uint32(16)
+        t = np.uint32(t0 + i)
+        pr = _bytes_le(philox4x32((q, n & np.uint32(~np.uint32(4)), t, np.uint32(bag)), _key(seed), rounds))       # [N, Q, 16]
+        rf = _bytes_le(philox4x32((refq, n & np.uint32(~np.uint32(12)), t, np.uint32(bag)), _key(seed), rounds))   # [N, Q, 16]
+        P = np.take_along_axis(pr, 8 * half[:, :, None] + e, axis=2)          # [N, Q, 8]
+        R = np.take_along_axis(rf, ridx[:, :, None], axis=2)                  # [N, Q, 1]
+        lanes = (P << np.uint32(8)) | R
         keep[i] = ((lanes & np.uint32(0x7FFF)) >= np.uint32(thr)).reshape(N, L)
     return keep
 
