@@ -43,9 +43,9 @@ constexpr int TC_THREADS = (MMA_WARP + NMMA) * 32;
 
 constexpr uint32_t SM_W = 0;
 constexpr uint32_t SM_RING = SM_W + NSLICE * SLICE_BYTES_W;        // 139264: 8 slots x 8 KB
-constexpr uint32_t SM_XCH = SM_RING + NSLICE * SLICE_BYTES_A;      // 204800: [2][64][4] floats
-constexpr uint32_t SM_BAR = SM_XCH + 2 * HALF_ROWS * MAXC * 4;     // 206848
-constexpr uint32_t SM_TOTAL = SM_BAR + 1024;                       // 207872 <= 232448 (227 KB)
+constexpr uint32_t SM_XCH = SM_RING + NSLICE * SLICE_BYTES_A;      // 204800: [2][64][2 x 4] floats (partial sums | logit multipliers)
+constexpr uint32_t SM_BAR = SM_XCH + 2 * HALF_ROWS * 2 * MAXC * 4; // 208896
+constexpr uint32_t SM_TOTAL = SM_BAR + 1024;                       // 209920 <= 232448 (227 KB)
 
 // where the feature keep-masks come from
 enum : int {
@@ -574,28 +574,40 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(tempty_leader + (tc & (NMMA - 1)) * 8);
         TRACE(tc, 2);
-        // combine the two hidden-unit halves of each patch row
-        float* x = xch + ((tc & 1) * HALF_ROWS + r) * MAXC;
+        // combine the two hidden-unit halves of each patch row.  The warps of the upper half also draw
+        // the logit-dropout multipliers (one Philox call per row and sample), the warps of the lower half
+        // do the global stores: the work left after the TMEM drain is split between the two warp pairs
+        // (= between SM sub-partitions 0,1 and 2,3, which all host two producer warps).
+        float* x = xch + ((tc & 1) * HALF_ROWS + r) * (2 * MAXC);
         if (half == 1) {
+          float mult[MAXC] = {0.f, 0.f, 0.f, 0.f};
+          if (valid) {
+            const uint32_t tg = (uint32_t)(P.t_offset + t);
+            uint4 rnd = make_uint4(0, 0, 0, 0);
+            if constexpr (!INJECT)
+              rnd = attn_words<ROUNDS>(0u, (uint32_t)(td.n0 + trow), tg, (uint32_t)(P.bag_offset + td.gbag), P.key);
 #pragma unroll
-          for (int c = 0; c < NOUT; ++c) x[c] = acc[c];
+            for (int c = 0; c < NOUT; ++c) {
+              const int head = P.head0 + c;
+              bool keep;
+              if constexpr (!INJECT) keep = attn_keep_from(rnd, head, P.thr_a);
+              else keep = (P.inj_attn[((size_t)t * P.C + head) * (P.Rp >> 5) + (g >> 5)] >> (g & 31)) & 1u;
+              mult[c] = keep ? P.sa : 0.f;
+            }
+          }
+          *reinterpret_cast<float4*>(x) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          *reinterpret_cast<float4*>(x + MAXC) = make_float4(mult[0], mult[1], mult[2], mult[3]);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (half == 0 && valid) {
-          const uint32_t tg = (uint32_t)(P.t_offset + t);
-          uint4 rnd = make_uint4(0, 0, 0, 0);
-          if constexpr (!INJECT)
-            rnd = attn_words<ROUNDS>(0u, (uint32_t)(td.n0 + trow), tg, (uint32_t)(P.bag_offset + td.gbag), P.key);
+          const float4 xs = *reinterpret_cast<const float4*>(x), xm = *reinterpret_cast<const float4*>(x + MAXC);
+          const float part[MAXC] = {xs.x, xs.y, xs.z, xs.w}, mult[MAXC] = {xm.x, xm.y, xm.z, xm.w};
 #pragma unroll
           for (int c = 0; c < NOUT; ++c) {
             const int head = P.head0 + c;
-            float logit = acc[c] + x[c] + P.epi.bw[c];
-            bool keep;
-            if constexpr (!INJECT) keep = attn_keep_from(rnd, head, P.thr_a);
-            else keep = (P.inj_attn[((size_t)t * P.C + head) * (P.Rp >> 5) + (g >> 5)] >> (g & 31)) & 1u;
-            logit = keep ? logit * P.sa : 0.f;           // a dropped logit is 0, not -inf (model.py:291,305)
+            const float logit = acc[c] + part[c] + P.epi.bw[c];
             const size_t o = ((size_t)t * P.C + head) * P.Rp + g;
-            P.logits[o] = logit;
+            P.logits[o] = mult[c] != 0.f ? logit * mult[c] : 0.f;   // a dropped logit is 0, not -inf (model.py:291,305)
             P.scores[o] = (__uint_as_float(sc[c]) + __uint_as_float(sc[4 + c])) * P.sf;
           }
         }
