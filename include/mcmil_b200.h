@@ -150,6 +150,18 @@ int mcmil_tile_nonzero_pct(const float* image /*[channels][H][W], channel 0 is r
 int mcmil_gather_tiles(const float* image, int channels, int H, int W, const int32_t* tiles, const int32_t* selected,
                        int n_selected, int patch, float* bag, void* stream);
 
+/* ---- deterministic forward + auxiliary loss ----------------------------------------
+ * The eval-mode forward of the head (model.py:211-253: no dropout, one pass) is mcmil_head_forward with
+ * T = 1 and p_f = p_a = 0 (threshold 0 keeps every element; Y[.][0][:] / A[0] are the outputs).
+ * mcmil_aux_pairwise_loss replaces AuxiliaryLoss.pairwise_distance_loss (model.py:405-426) as the model
+ * applies it per MC pass (model.py:318-326) or once (model.py:243-248):
+ *   A     DEVICE fp32 [T][C][R] (mcmil_head_forward's A)
+ *   loss  DEVICE fp32 [n_bags][T]:  scale * (is_positive ? max(margin - d, 0) : d),
+ *         d = || A[t][pos_head][bag rows] - A[t][neg_head][bag rows] + eps ||_2   (F.pairwise_distance)
+ * The reference uses pos_head = 1, neg_head = 0, margin = 1.0, scale = 0.5 (model.py:149-151), eps = 1e-6. */
+int mcmil_aux_pairwise_loss(const mcmil_plan_t* plan, const float* A, int pos_head, int neg_head, int is_positive,
+                            float margin, float scale, float eps, float* loss, void* stream);
+
 /* ---- measurement hook (bench.py): brackets the tcgen05 projection launch(es) of the next
  * `max_calls` mcmil_head_forward calls with CUDA events on the launching stream;
  * mcmil_profile_end synchronises them and returns the summed device time and the number of

@@ -40,6 +40,7 @@ SIGNATURES = {
     "mcmil_attnmap_stats": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mcmil_tile_nonzero_pct": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
     "mcmil_gather_tiles": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "mcmil_aux_pairwise_loss": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp]),
     "mcmil_profile_begin": (_i, [_i]),
     "mcmil_profile_end": (_i, [C.POINTER(_dbl), C.POINTER(_i)]),
 }

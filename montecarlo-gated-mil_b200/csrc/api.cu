@@ -285,6 +285,15 @@ int mcmil_welford_unpack(const double* packed, int n, float* mean, float* m2, vo
   return e == cudaSuccess ? 0 : cuda_fail(e, "mcmil_welford_unpack");
 }
 
+int mcmil_aux_pairwise_loss(const mcmil_plan_t* plan, const float* A, int pos_head, int neg_head, int is_positive,
+                            float margin, float scale, float eps, float* loss, void* stream) {
+  if (!plan || !A || !loss) return fail(MCMIL_E_BADARG, "mcmil_aux_pairwise_loss: null argument");
+  if (pos_head < 0 || pos_head >= plan->C || neg_head < 0 || neg_head >= plan->C)
+    return fail(MCMIL_E_BADARG, "mcmil_aux_pairwise_loss: head index out of range");
+  cudaError_t e = launch_aux_pairwise(*plan, A, pos_head, neg_head, is_positive, margin, scale, eps, loss, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "mcmil_aux_pairwise_loss");
+}
+
 int mcmil_export_masks(const mcmil_plan_t* plan, int t_offset, int bag_offset, uint64_t seed, int philox_rounds,
                        float p_f, float p_a, uint32_t* feat_bits, uint32_t* attn_bits, void* stream) {
   if (!plan) return fail(MCMIL_E_BADARG, "mcmil_export_masks: null plan");

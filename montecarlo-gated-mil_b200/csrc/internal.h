@@ -88,6 +88,8 @@ cudaError_t launch_gather_tiles(const float* img, int Cimg, int Himg, int W, con
                                 const int32_t* sel, int n_sel, int patch, float* bag, cudaStream_t st);
 cudaError_t launch_welford_pack(const float* mean, const float* m2, double count, int n, double* packed,
                                 cudaStream_t st);
+cudaError_t launch_aux_pairwise(const Plan& p, const float* A, int pos, int neg, int is_positive, float margin,
+                                float scale, float eps, float* loss, cudaStream_t st);
 cudaError_t launch_welford_unpack(const double* packed, int n, float* mean, float* m2, cudaStream_t st);
 
 }  // namespace mcmil

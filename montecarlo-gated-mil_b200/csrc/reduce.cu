@@ -206,4 +206,40 @@ cudaError_t launch_welford_unpack(const double* packed, int n, float* mean, floa
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ auxiliary loss (model.py:318-326, 405-426)
+// One CTA per (bag, sample): d = || A[t,pos,:] - A[t,neg,:] + eps ||_2 over the bag's patches
+// (F.pairwise_distance adds eps to the difference), loss = scale * (positive ? max(margin - d, 0) : d).
+// Fixed-order tree reduction: bit-deterministic.
+__global__ void __launch_bounds__(256) aux_pairwise_kernel(const float* __restrict__ A, const int* __restrict__ cu, int T,
+                                                           int C, int R, int pos, int neg, int is_positive, float margin,
+                                                           float scale, float eps, float* __restrict__ loss) {
+  const int b = blockIdx.x, t = blockIdx.y;
+  const int r0 = cu[b], r1 = cu[b + 1];
+  const float* ap = A + ((size_t)t * C + pos) * R;
+  const float* an = A + ((size_t)t * C + neg) * R;
+  float acc = 0.f;
+  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+    const float d = ap[r] - an[r] + eps;
+    acc = fmaf(d, d, acc);
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w];
+    const float d = sqrtf(s);
+    loss[(size_t)b * T + t] = scale * (is_positive ? fmaxf(margin - d, 0.f) : d);
+  }
+}
+cudaError_t launch_aux_pairwise(const Plan& p, const float* A, int pos, int neg, int is_positive, float margin,
+                                float scale, float eps, float* loss, cudaStream_t st) {
+  aux_pairwise_kernel<<<dim3(p.n_bags, p.T), 256, 0, st>>>(A, p.d_cu, p.T, p.C, p.R, pos, neg, is_positive, margin, scale,
+                                                          eps, loss);
+  return cudaGetLastError();
+}
+
 }  // namespace mcmil

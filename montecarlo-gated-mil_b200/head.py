@@ -246,6 +246,39 @@ def mc_head(weights: HeadWeights, H: torch.Tensor, T: int, seed: int = 0,
     return MCHeadResult(Y, pm, pq, am, aq, A, T, cu, launches)
 
 
+def head_forward_eval(weights: HeadWeights, H: torch.Tensor, cu_seqlens: Optional[Sequence[int]] = None):
+    """Deterministic (eval-mode) forward of the head, /root/reference/model.py:216-240 with the dropout
+    modules inactive: one pass of the same fused kernels with every mask element kept.
+    Returns (Y (n_bags, C) logits, A (C, R) attention)."""
+    res = mc_head(weights, H, 1, seed=0, p_f=0.0, p_a=0.0, cu_seqlens=cu_seqlens, return_attention=True)
+    return res.Y[:, 0, :], res.A[0]
+
+
+def aux_pairwise_loss(A: torch.Tensor, is_positive: bool, cu_seqlens: Optional[Sequence[int]] = None,
+                      pos_head: int = 1, neg_head: int = 0, margin: float = 1.0, scale: float = 0.5,
+                      eps: float = 1e-6) -> torch.Tensor:
+    """scale * AuxiliaryLoss('pairwise')(A[:, pos], A[:, neg], is_positive) per (bag, MC pass):
+    /root/reference/model.py:243-248 (forward) and :318-326 (one value per pass), loss of :415-426.
+    A (T, C, R) fp32 CUDA (the `A` of mc_head); returns (n_bags, T) fp32 CUDA."""
+    lib = _lib.load()
+    if not isinstance(A, torch.Tensor) or A.device.type != "cuda" or A.dim() != 3:
+        raise RuntimeError("aux_pairwise_loss: A must be a (T, C, R) CUDA tensor (no CPU fallback)")
+    if A.dtype != torch.float32 or not A.is_contiguous():
+        raise ValueError("aux_pairwise_loss: A must be contiguous float32")
+    T, C_, R = A.shape
+    if not (0 <= pos_head < C_ and 0 <= neg_head < C_):
+        raise ValueError("aux_pairwise_loss: needs the two heads it compares (the reference uses heads 1 and 0)")
+    cu = np.array([0, R], np.int32) if cu_seqlens is None else np.asarray(cu_seqlens, dtype=np.int32)
+    dev = A.device
+    plan = _get_plan(cu, T, C_, dev)
+    with torch.cuda.device(dev):
+        out = torch.empty((plan.n_bags, T), dtype=torch.float32, device=dev)
+        _lib.check(lib.mcmil_aux_pairwise_loss(plan._h, _ptr(A), int(pos_head), int(neg_head), int(bool(is_positive)),
+                                               float(margin), float(scale), float(eps), _ptr(out), _stream_ptr(dev)),
+                   "mcmil_aux_pairwise_loss")
+    return out
+
+
 def export_masks(T: int, R_or_cu, num_classes: int, seed: int, p_f: float, p_a: float,
                  t_offset: int = 0, bag_offset: int = 0, device="cuda", philox_rounds: int = 10):
     """The keep-bits the in-kernel Philox draws: (feat (T,R,16) int32, attn (T,C,ceil(R/32)) int32)."""

@@ -1,11 +1,11 @@
 """Drop-in module: same constructor, parameter names / state_dict keys and `mc_inference`
 signature as the reference `MultiHeadGatedAttentionMIL` (/root/reference/model.py:134-328).
 
-Only the MC-dropout head is B200-native: the ResNet feature extractor runs once per bag in
-PyTorch (north_star; /root/reference/model.py:276-277) and its (N,512) output goes straight
-into the fused CUDA head.  `forward` (training / deterministic eval, /root/reference/
-model.py:211-253) is kept as plain torch so existing training scripts still run; it is not
-the accelerated path.
+Only the head is B200-native: the ResNet feature extractor runs once per bag in PyTorch
+(north_star; /root/reference/model.py:276-277) and its (N,512) output goes straight into the
+fused CUDA head — T MC-dropout passes for `mc_inference`, one all-keep pass for the eval-mode
+`forward` (/root/reference/model.py:211-253).  `forward` in training mode keeps the plain
+torch graph (autograd) so existing training scripts still run.
 """
 from __future__ import annotations
 
@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .head import HeadWeights, MCHeadResult, mc_head
+from .head import HeadWeights, MCHeadResult, aux_pairwise_loss, head_forward_eval, mc_head
 
 
 class Identity(nn.Module):
@@ -57,9 +57,17 @@ class MultiHeadGatedAttentionMIL(nn.Module):
         self._packed = None          # (HeadWeights, version key)
         self.mc_seed = 0             # Philox key of the next mc_inference call (auto-incremented)
         self.last_result: MCHeadResult | None = None
+        self.fused_eval = True       # eval-mode forward() through the fused head (forward_eval_fused)
 
-    # ------------------------------------------------------------------ plain-torch forward (not the hot path)
+    # ------------------------------------------------------------------ forward (model.py:211-253)
+    AUX_MARGIN, AUX_SCALE = 1.0, 0.5          # AuxiliaryLoss(loss_type='pairwise', margin=1.0, scale=.5), model.py:149-151
+
     def forward(self, x, targets=None):
+        """Training keeps the plain-torch graph (autograd).  Deterministic inference — eval mode, grad
+        disabled, CUDA input, as in the reference's validate / test loops (net_utils.py:82-114,160-192) —
+        runs the head through the fused kernels (`forward_eval_fused`)."""
+        if self.fused_eval and not self.training and not torch.is_grad_enabled() and x.is_cuda:
+            return self.forward_eval_fused(x, targets)
         bs, n, ch, w, h = x.shape
         H = self.feature_extractor(x.view(bs * n, ch, w, h))
         H = self.feature_dropout(H).view(bs, n, -1)
@@ -79,6 +87,26 @@ class MultiHeadGatedAttentionMIL(nn.Module):
             d = F.pairwise_distance(A_all[:, 1, :], A_all[:, 0, :])
             # model.py:405-426 (pairwise, margin 1.0, scale 0.5): push the heads apart on positives
             aux = 0.5 * (torch.clamp(1.0 - d, min=0).mean() if targets.item() == 1 else d.mean())
+        return Y, A_all, aux
+
+    def forward_eval_fused(self, x, targets=None):
+        """model.py:211-253 in eval mode (dropout inactive): extractor in torch, then ONE pass of the fused
+        head with all-keep masks; the auxiliary loss (model.py:243-248) by mcmil_aux_pairwise_loss.
+        Returns (Y (bs, C), A_all (bs, C, n), auxiliary_loss or None) like the reference."""
+        bs, n = x.shape[:2]
+        if x.device.type != "cuda":
+            raise RuntimeError("forward_eval_fused needs CUDA tensors (there is no CPU fallback)")
+        with torch.no_grad():
+            H = self.feature_extractor(x.view(bs * n, *x.shape[2:])).view(bs * n, -1).float().contiguous()
+            cu = [i * n for i in range(bs + 1)]
+            Y, A = head_forward_eval(self._head_weights(x.device), H, cu)          # (bs, C), (C, bs*n)
+            A_all = A.view(self.num_classes, bs, n).permute(1, 0, 2).contiguous()   # (bs, C, n)
+            aux = None
+            if targets is not None:
+                if self.num_classes < 2:
+                    raise RuntimeError("the auxiliary loss compares heads 1 and 0 (model.py:246-247)")
+                aux = aux_pairwise_loss(A.view(1, self.num_classes, bs * n), targets.item() == 1, cu,
+                                        margin=self.AUX_MARGIN, scale=self.AUX_SCALE).mean()   # torch.mean over bs
         return Y, A_all, aux
 
     # ------------------------------------------------------------------ the B200 hot path
@@ -126,13 +154,19 @@ class MultiHeadGatedAttentionMIL(nn.Module):
         """Same contract as the reference (model.py:256-328): returns
         (Y (N,1,C) logits, A (N,1,C,num_instances)); `legacy_tuple=True` appends the third
         value (None) that the reference's committed callers unpack (infer.py:191,
-        net_utils.py:126,205).  `targets` is accepted and ignored: the reference computes
-        the auxiliary losses and then discards them (model.py:318-328).  The Welford
+        net_utils.py:126,205): the list of N per-pass auxiliary losses when `targets` is given
+        (model.py:318-326; computed by mcmil_aux_pairwise_loss), else None.  The Welford
         statistics of the same call are kept in `self.last_result`."""
         res = self.mc_inference_stats(input_tensor, N=N, device=device, seed=seed, return_attention=True)
         Y = res.Y.permute(1, 0, 2).contiguous()                     # (N, 1, C)
         A = res.A.unsqueeze(1)                                      # (N, 1, C, n)
-        return (Y, A, None) if legacy_tuple else (Y, A)
+        if not legacy_tuple:
+            return Y, A
+        losses = None
+        if targets is not None and self.num_classes >= 2:           # model.py:318-326: one loss per MC pass
+            per_pass = aux_pairwise_loss(res.A, targets.item() == 1, margin=self.AUX_MARGIN, scale=self.AUX_SCALE)[0]
+            losses = list(per_pass.unbind(0))
+        return Y, A, losses
 
 
 def deactivate_batchnorm(m):

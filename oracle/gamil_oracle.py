@@ -135,6 +135,23 @@ def mc_head_oracle(sd: dict, H: np.ndarray, keep_f: np.ndarray, keep_a: np.ndarr
     return finish_stats(Y, A)
 
 
+def forward_oracle(sd: dict, H: np.ndarray) -> dict:
+    """Eval-mode forward of the head (model.py:216-240, dropout modules inactive): Y (C), A (C,N)."""
+    H = np.asarray(H, np.float64)
+    N, L = H.shape
+    C = num_classes_of(sd)
+    st = mc_head_oracle(sd, H, np.ones((1, N, L), np.uint8), np.ones((1, C, N), np.uint8), 0.0, 0.0)
+    return {"Y": st["Y"][0], "A": st["A"][0]}
+
+
+def aux_pairwise_loss(a_pos: np.ndarray, a_neg: np.ndarray, is_positive: bool, margin: float = 1.0,
+                      scale: float = 0.5, eps: float = 1e-6) -> np.ndarray:
+    """scale * AuxiliaryLoss.pairwise_distance_loss (model.py:415-426; scale/margin of model.py:149-151) over
+    the last axis; F.pairwise_distance(x1, x2) = ||x1 - x2 + eps||_2."""
+    d = np.sqrt(((np.asarray(a_pos, np.float64) - np.asarray(a_neg, np.float64) + eps) ** 2).sum(axis=-1))
+    return scale * (np.maximum(margin - d, 0.0) if is_positive else d)
+
+
 def finish_stats(Y: np.ndarray, A: np.ndarray) -> dict:
     Y = np.asarray(Y, np.float64)
     A = np.asarray(A, np.float64)

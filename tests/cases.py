@@ -12,7 +12,25 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def golden_names():
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    return [n for n in names if not n.startswith("patcher_")]      # patcher_*: tests/test_patcher.py
+    return [n for n in names if not n.startswith(("patcher_", "fwd_"))]   # patcher_*: test_patcher.py, fwd_*: FwdCase
+
+
+def forward_golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "fwd_*.npz")))
+
+
+class FwdCase:
+    """Deterministic forward + auxiliary loss outputs of the live reference (make_golden_forward.py)."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.name = name
+        self.N, self.C, shared, self.wseed, self.hseed, self.mseed, self.T = (int(v) for v in z["meta"])
+        self.shared = bool(shared)
+        self.peaky, self.hscale = (float(v) for v in z["fmeta"])
+        self.ref = {k: z[k] for k in z.files if k not in ("meta", "fmeta")}
+        self.sd = G.make_weights(self.wseed, self.C, self.shared, peaky=self.peaky)
+        self.H = G.make_features(self.hseed, self.N, scale=self.hscale)
 
 
 class Case:

@@ -11,7 +11,7 @@ import torch
 
 from oracle import gamil_oracle as G
 from oracle import philox as PX
-from tests.cases import Case, golden_names
+from tests.cases import Case, FwdCase, forward_golden_names, golden_names
 
 pytestmark = pytest.mark.gpu
 
@@ -250,6 +250,70 @@ def test_module_dropin_interface(mm):
         assert m.last_result.count == T
         with pytest.raises(RuntimeError):
             m.mc_inference(torch.zeros(2, 4, 512, 1, 1), N=2, device="cuda")            # bs != 1, model.py:309
+
+
+@pytest.mark.parametrize("name", forward_golden_names())
+def test_forward_eval_and_aux_loss_vs_reference(mm, name):
+    """SURVEY §8f-2 through the C-ABI: one all-keep pass of the fused head = the reference's eval-mode forward
+    (model.py:211-253); mcmil_aux_pairwise_loss = scale * AuxiliaryLoss (model.py:243-248, 318-326)."""
+    c = FwdCase(name)
+    dev = torch.device("cuda")
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in c.sd.items()}, dev)
+    H = torch.from_numpy(c.H).to(dev)
+    Y, A = mm.head_forward_eval(w, H)
+    Yn, An = Y[0].double().cpu().numpy(), A.double().cpu().numpy()
+    P = np.exp(Yn - Yn.max()); P /= P.sum()
+    Pr = np.exp(c.ref["Y"].astype(np.float64) - c.ref["Y"].max()); Pr /= Pr.sum()
+    assert np.abs(P / Pr - 1).max() < PROB_RTOL
+    assert np.abs(Yn - c.ref["Y"]).max() < 2e-3 * max(1.0, np.abs(c.ref["Y"]).max())
+    assert np.abs(An - c.ref["A"]).max() < ATTN_ATOL and np.abs(An / c.ref["A"] - 1).max() < 1e-2
+    assert abs(An.sum(-1) - 1).max() < 1e-5
+    if c.C < 2:
+        return
+    A1 = A.view(1, c.C, c.N).contiguous()
+    for pos, key in ((True, "aux_pos"), (False, "aux_neg")):
+        got = float(mm.aux_pairwise_loss(A1, pos)[0, 0])
+        assert abs(got - float(c.ref[key])) < 1e-4 + 1e-3 * abs(float(c.ref[key])), key
+        # the kernel itself, fed the reference's attention: fp32 rounding only
+        Aref = torch.from_numpy(c.ref["A"]).to(dev).view(1, c.C, c.N).contiguous()
+        assert abs(float(mm.aux_pairwise_loss(Aref, pos)[0, 0]) - float(c.ref[key])) < 2e-7
+    # per-pass losses of mc_inference (model.py:318-326) with the same Philox masks the golden file used
+    res = mm.mc_head(w, H, c.T, seed=c.mseed, return_attention=True)
+    for pos, key in ((True, "mc_aux_pos"), (False, "mc_aux_neg")):
+        got = mm.aux_pairwise_loss(res.A, pos)[0].double().cpu().numpy()
+        assert np.abs(got - c.ref[key]).max() < 1e-4 + 1e-3 * np.abs(c.ref[key]).max(), key
+
+
+def test_module_forward_eval_fused_matches_torch_path(mm):
+    """Module level: eval-mode forward() routes through the fused head and agrees with the plain-torch graph
+    (the training path) on Y, A_all and the auxiliary loss; packed batches (bs > 1) included."""
+    import torch.nn as nn
+    dev = torch.device("cuda")
+    for shared, bs, n in ((True, 1, 150), (False, 3, 70)):
+        m = mm.MultiHeadGatedAttentionMIL(pretrained=False, shared_attention=shared)
+        m.feature_extractor = nn.Flatten()
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in G.make_weights(61, 2, shared).items()}, strict=False)
+        m = m.to(dev).eval()
+        x = torch.from_numpy(np.stack([G.make_features(700 + b, n) for b in range(bs)])).view(bs, n, 512, 1, 1).to(dev)
+        with torch.no_grad():
+            Yf, Af, _ = m(x)
+            m.fused_eval = False
+            Yt, At, _ = m(x)
+            m.fused_eval = True
+        assert Yf.shape == Yt.shape == (bs, 2) and Af.shape == At.shape == (bs, 2, n)
+        assert (Yf - Yt).abs().max() < 2e-3 and (Af - At).abs().max() < ATTN_ATOL
+        if bs == 1:                                   # targets.item() (model.py:244) needs one target
+            for tgt in (1, 0):
+                with torch.no_grad():
+                    lf = m(x, targets=torch.tensor([tgt], device=dev))[2]
+                    m.fused_eval = False
+                    lt = m(x, targets=torch.tensor([tgt], device=dev))[2]
+                    m.fused_eval = True
+                assert abs(float(lf) - float(lt)) < 1e-4
+            Y3 = m.mc_inference(x, N=5, device="cuda", targets=torch.tensor([1]), legacy_tuple=True, seed=3)
+            assert len(Y3) == 3 and len(Y3[2]) == 5 and all(t.numel() == 1 for t in Y3[2])
+        m.train()
+        assert m(x)[0].requires_grad                  # training keeps the torch graph
 
 
 def test_argument_errors(mm):

@@ -5,7 +5,7 @@ import pytest
 
 from oracle import gamil_oracle as G
 from oracle import philox as PX
-from tests.cases import Case, golden_names
+from tests.cases import Case, FwdCase, forward_golden_names, golden_names
 
 
 def test_philox_known_answers():
@@ -67,6 +67,24 @@ def test_oracle_matches_reference(name):
     assert np.abs(out["attn_mean"] - c.ref["attn_mean"]).max() < 1e-7
     rel = np.abs(out["attn_m2"] - c.ref["attn_m2"]) / (np.abs(c.ref["attn_m2"]) + 1e-30)
     assert rel.max() < 1e-3
+
+
+@pytest.mark.parametrize("name", forward_golden_names())
+def test_forward_and_aux_oracle_match_reference(name):
+    """eval-mode forward (model.py:211-253) and auxiliary loss (model.py:243-248, 318-326,
+    405-426) restatements vs the outputs of the live reference stored by make_golden_forward.py."""
+    c = FwdCase(name)
+    o = G.forward_oracle(c.sd, c.H)
+    assert np.abs(o["Y"] - c.ref["Y"]).max() < 5e-6
+    assert np.abs(o["A"] - c.ref["A"]).max() < 2e-7
+    if c.C >= 2:
+        assert abs(G.aux_pairwise_loss(o["A"][1], o["A"][0], True) - c.ref["aux_pos"]) < 1e-6
+        assert abs(G.aux_pairwise_loss(o["A"][1], o["A"][0], False) - c.ref["aux_neg"]) < 1e-6
+        kf = PX.feature_keep(c.mseed, 0, 0, c.T, c.N, 0.1)
+        ka = PX.attn_keep(c.mseed, 0, 0, c.T, c.N, c.C, 0.1)
+        A = G.mc_head_oracle(c.sd, c.H, kf, ka, 0.1, 0.1)["A"]
+        assert np.abs(G.aux_pairwise_loss(A[:, 1], A[:, 0], True) - c.ref["mc_aux_pos"]).max() < 1e-6
+        assert np.abs(G.aux_pairwise_loss(A[:, 1], A[:, 0], False) - c.ref["mc_aux_neg"]).max() < 1e-6
 
 
 def test_welford_sumform_merge():
