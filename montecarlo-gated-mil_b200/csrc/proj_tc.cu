@@ -112,10 +112,18 @@ __device__ __forceinline__ uint32_t bar_addr(uint32_t sbase, uint32_t slot) { re
 #define TRACE_DUMP(role)
 #endif
 // -DMCMIL_EXP_WAITSTATS: every warp of the first cluster reports the cycles it spent in barrier waits
+#ifndef MCMIL_RELAXED_NS_TEMPTY
+#define MCMIL_RELAXED_NS_TEMPTY 256     // issue warps waiting for the accumulator buffer (idle ~2 samples out of 4)
+#endif
+#ifndef MCMIL_RELAXED_NS_TFULL
+#define MCMIL_RELAXED_NS_TFULL 128      // epilogue warps waiting for the next accumulator (double buffered)
+#endif
 #ifdef MCMIL_EXP_WAITSTATS
 #define WAIT_T(acc, bar, parity) do { const long long w0_ = clock64(); mbar_wait(bar, parity); acc += clock64() - w0_; } while (0)
+#define WAIT_R(acc, bar, parity, ns) do { const long long w0_ = clock64(); if ((ns) > 0) mbar_wait_relaxed(bar, parity, ns); else mbar_wait(bar, parity); acc += clock64() - w0_; } while (0)
 #else
 #define WAIT_T(acc, bar, parity) mbar_wait(bar, parity)
+#define WAIT_R(acc, bar, parity, ns) do { if ((ns) > 0) mbar_wait_relaxed(bar, parity, ns); else mbar_wait(bar, parity); } while (0)
 #endif
 
 // keep -> all-ones half lanes.  r holds two 16-bit uniform lanes; an element is kept iff
@@ -261,7 +269,17 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
   // stream; the features (producers) and the logits / scores planes (epilogue; still read by the
   // previous call's reduction kernels) may only be touched after griddepcontrol.wait.
   grid_dep_launch();
+  // Register file: 16 warps x 128 registers at launch.  The four issue warps (one warpgroup) need ~40 and hand
+  // the rest to the two producer warpgroups, whose 64-register feature tile + Philox state otherwise forces
+  // ptxas to rematerialise addresses and spill inside the K-slice loop.
+#ifndef MCMIL_NO_SETMAXNREG
+  constexpr int REGS_MMA = 56, REGS_PRODUCER = 160;
+  static_assert(128 + 2 * REGS_PRODUCER + REGS_MMA <= 512, "per sub-partition: 1 epilogue + 2 producer + 1 issue warp");
+#endif
   if (warp >= MMA_WARP) {
+#ifndef MCMIL_NO_SETMAXNREG
+    reg_dealloc<REGS_MMA>();
+#endif
     // ------------------------------------------------------------ TMA loader: this CTA's W rows, once
     if (warp == LOAD_WARP && lane == 0) {
       const uint32_t wloc = bar_addr(sbase, B_WLOC);
@@ -298,7 +316,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         TRACE(NMMA * j + q, 0);
         // buffer tc & 1 was last used by sample tc - 2, whose epilogue arrives on TEMPTY[(tc - 2) % NMMA]:
         // that is phase j of TEMPTY[q - 2] for q >= 2, phase j - 1 of TEMPTY[q + NMMA - 2] otherwise
-        WAIT_T(wait_b, bar_addr(sbase, B_TEMPTY + ((q + NMMA - 2) & (NMMA - 1))), q >= 2 ? (j & 1) : ((j & 1) ^ 1));
+        WAIT_R(wait_b, bar_addr(sbase, B_TEMPTY + ((q + NMMA - 2) & (NMMA - 1))), q >= 2 ? (j & 1) : ((j & 1) ^ 1), MCMIL_RELAXED_NS_TEMPTY);
         TRACE(NMMA * j + q, 1);
         tc_fence_after();
 #pragma unroll 1
@@ -344,16 +362,22 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     // chunks per warp and slice = 4 chunks per thread).  The two producer warps that share an
     // SM sub-partition belong to different teams.  The ring is a full sample deep (slot = K-slice),
     // so a warp only ever waits for the MMAs of the PREVIOUS sample.
+#ifndef MCMIL_NO_SETMAXNREG
+    reg_alloc<REGS_PRODUCER>();
+#endif
     const int pw = warp - PRODUCER_WARP0;
     const int team = pw >> 2, wt = pw & 3;           // warps of one team sit on the four different schedulers
-    const uint32_t full_leader = mapa(bar_addr(sbase, B_FULL), 0);
-    const uint32_t thr2 = P.thr_f | (P.thr_f << 16);
+    // thread-constant addresses, pinned in registers (see ptx::pin)
+    const uint32_t full_team = pin(mapa(bar_addr(sbase, B_FULL), 0) + (uint32_t)team * 8u);    // + (set + TEAMS*si) * 8
+    const uint32_t empty_team = pin(bar_addr(sbase, B_EMPTY) + (uint32_t)team * 8u);
+    const uint32_t thr2 = pin(P.thr_f | (P.thr_f << 16));
     const int chunk = lane & 7;
     int rowi[4]; uint32_t off[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       rowi[i] = wt * 16 + i * 4 + (lane >> 3);
-      off[i] = (uint32_t)rowi[i] * 128u + (uint32_t)((chunk ^ (rowi[i] & 7)) << 4);
+      off[i] = pin(sbase + SM_RING + (uint32_t)team * SLICE_BYTES_A + (uint32_t)rowi[i] * 128u +
+                   (uint32_t)((chunk ^ (rowi[i] & 7)) << 4));             // ring address of slice `team`; + TEAMS*si slices
     }
     uint32_t tc = 0;                                  // samples processed so far by this pair
     bool slot_free = false;                           // early probe result for the next ring slot
@@ -439,15 +463,15 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 #ifndef MCMIL_EXP_PRODUCER_ONLY
           TRACE(tc, 4 * si);
 #ifndef MCMIL_NO_EARLY_PROBE
-          if (tc > 0 && !slot_free) WAIT_T(wait_a, bar_addr(sbase, B_EMPTY + empty_set + s), empty_parity);
+          if (tc > 0 && !slot_free) WAIT_T(wait_a, empty_team + (empty_set + TEAMS * si) * 8, empty_parity);
 #else
-          if (tc > 0) WAIT_T(wait_a, bar_addr(sbase, B_EMPTY + empty_set + s), empty_parity);
+          if (tc > 0) WAIT_T(wait_a, empty_team + (empty_set + TEAMS * si) * 8, empty_parity);
 #endif
           TRACE(tc, 4 * si + 1);
 #endif
 #ifdef MCMIL_EXP_MMA_ONLY       // experiment: no producer work at all, the MMA / epilogue chain runs flat out
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(full_leader + (full_set + s) * 8);
+          if (lane == 0) mbar_arrive_cluster(full_team + (full_set + TEAMS * si) * 8);
           continue;
 #endif
           uint4 nxt[2], ref_nxt = ref;
@@ -480,8 +504,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
               m.z = (bits & 16u ? 0x0000FFFFu : 0u) | (bits & 32u ? 0xFFFF0000u : 0u);
               m.w = (bits & 64u ? 0x0000FFFFu : 0u) | (bits & 128u ? 0xFFFF0000u : 0u);
             }
-            *reinterpret_cast<uint4*>(smem + SM_RING + s * SLICE_BYTES_A + off[i]) =
-                make_uint4(h.x & m.x, h.y & m.y, h.z & m.z, h.w & m.w);
+            sts128(off[i] + (uint32_t)(TEAMS * si) * SLICE_BYTES_A, make_uint4(h.x & m.x, h.y & m.y, h.z & m.z, h.w & m.w));
           }
 #if !defined(MCMIL_NO_EARLY_PROBE) && !defined(MCMIL_EXP_PRODUCER_ONLY)
           // Probe the barrier of the NEXT slot now: the answer (an ~200-cycle round trip through the
@@ -491,8 +514,8 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
             const bool last = si == TEAM_SLICES - 1;
             const uint32_t nset = last ? full_set : empty_set;                       // empty_set of sample tc+1 == full_set of tc
             const uint32_t npar = last ? ((tc >> LOGM) & 1) : empty_parity;
-            const int ns = last ? team : s + TEAMS;
-            slot_free = (last || tc > 0) && mbar_test_wait(bar_addr(sbase, B_EMPTY + nset + ns), npar);
+            const int nsi = last ? 0 : si + 1;
+            slot_free = (last || tc > 0) && mbar_test_wait(empty_team + (nset + TEAMS * nsi) * 8, npar);
           }
 #endif
           if constexpr (DRAW) {
@@ -507,7 +530,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
           TRACE(tc, 4 * si + 2);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(full_leader + (full_set + s) * 8);
+          if (lane == 0) mbar_arrive_cluster(full_team + (full_set + TEAMS * si) * 8);
           TRACE(tc, 4 * si + 3);
           if constexpr (DRAW) { rnd[0] = nxt[0]; rnd[1] = nxt[1]; ref = ref_nxt; }
         }
@@ -550,7 +573,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       for (int t = t_begin; t < t_end; ++t, ++tc) {
         const uint32_t buf = tc & 1;
         TRACE(tc, 0);
-        WAIT_T(wait_a, bar_addr(sbase, B_TFULL + buf), (tc >> 1) & 1);
+        WAIT_R(wait_a, bar_addr(sbase, B_TFULL + buf), (tc >> 1) & 1, MCMIL_RELAXED_NS_TFULL);
         TRACE(tc, 1);
         tc_fence_after();
         float acc[MAXC] = {0.f, 0.f, 0.f, 0.f};

@@ -82,6 +82,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #endif
 }
 
+// st.shared.v4 at a 32-bit shared address
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// makes a value opaque to the compiler: it must live in a register instead of being recomputed
+// (ptxas otherwise rematerialises thread-constant addresses inside every K-slice of the producer loop)
+__device__ __forceinline__ uint32_t pin(uint32_t v) { asm volatile("mov.u32 %0, %0;" : "+r"(v)); return v; }
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -92,6 +100,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+
+// Long waits of warps that share a scheduler with busy warps: poll with plain nanosleep in between.
+// (mbarrier.try_wait's NANOSLEEP.SYNCS wakes on every barrier event of the SM, i.e. every ~100 cycles
+// here, and each wake-up costs ~7 issue slots: the idle issue / epilogue warps were 17 % of all issued
+// instructions.)  Costs up to `ns` of wake-up latency: only for waits with that much slack.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
+#ifndef MCMIL_UNBOUNDED_WAITS
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    asm volatile("nanosleep.u32 %0;" :: "r"(ns));
+    if (++spins > (1u << 24)) { __trap(); }
+  }
+#else
+  while (!mbar_test_wait(bar, parity)) asm volatile("nanosleep.u32 %0;" :: "r"(ns));
+#endif
+}
+
+// ---------------------------------------------------------------- register re-allocation between warpgroups
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
+template <int N> __device__ __forceinline__ void reg_alloc()   { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
 
 // ---------------------------------------------------------------- PDL
 __device__ __forceinline__ void grid_dep_wait()    { asm volatile("griddepcontrol.wait;" ::: "memory"); }
