@@ -188,9 +188,17 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// One TMEM lane half of the gate epilogue.  Hidden units are processed in pairs (d, d+1) with packed fp32x2
+// FMAs (FFMA2): pre-activations, the gate product and the w_c dot products each take one instruction per pair,
+// 3 + NOUT FMA-type + 4 MUFU instructions per pair instead of 2 x (3 + NOUT) + 4.  acc2[c] holds the
+// (even d, odd d) partial sums of head c.
 template <int HALF, int NOUT, bool DEBUG>
 __device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tbuf, float (&acc)[MAXC],
                                               float* dbg_row) {
+  uint64_t acc2[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) acc2[c] = 0ull;
+  const uint64_t sf2 = pack2(P.sf, P.sf), hsf2 = pack2(P.hsf, P.hsf);
 #pragma unroll
   for (int part = 0; part < 2; ++part) {            // MMA "a" columns, then MMA "b" columns
     const uint32_t tcol = tbuf + (part == 0 ? TM_A : TM_B);
@@ -214,15 +222,28 @@ __device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tbuf
       continue;
 #endif
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < 16; i += 2) {
         const int d = 64 * part + 32 * HALF + 16 * j + i;
-        const float av = tanh_approx(fmaf(__uint_as_float(v[i]), P.sf, P.epi.bv[d]));
-        const float au = tanh_approx(fmaf(__uint_as_float(u[i]), P.hsf, P.epi.hbu[d]));
-        const float g2 = fmaf(av, au, av);            // 2 * tanh(.) * sigmoid(.)
+        const uint64_t xv = fma2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sf2,
+                                 pack2(P.epi.bv[d], P.epi.bv[d + 1]));
+        const uint64_t xu = fma2(pack2(__uint_as_float(u[i]), __uint_as_float(u[i + 1])), hsf2,
+                                 pack2(P.epi.hbu[d], P.epi.hbu[d + 1]));
+        float xv0, xv1, xu0, xu1;
+        unpack2(xv, xv0, xv1);
+        unpack2(xu, xu0, xu1);
+        const uint64_t av = pack2(tanh_approx(xv0), tanh_approx(xv1));
+        const uint64_t au = pack2(tanh_approx(xu0), tanh_approx(xu1));
+        const uint64_t g2 = fma2(av, au, av);          // 2 * tanh(.) * sigmoid(.)
 #pragma unroll
-        for (int c = 0; c < NOUT; ++c) acc[c] = fmaf(g2, P.epi.hw[c][d], acc[c]);
+        for (int c = 0; c < NOUT; ++c) acc2[c] = fma2(g2, pack2(P.epi.hw[c][d], P.epi.hw[c][d + 1]), acc2[c]);
       }
     }
+  }
+#pragma unroll
+  for (int c = 0; c < NOUT; ++c) {
+    float lo, hi;
+    unpack2(acc2[c], lo, hi);
+    acc[c] += lo + hi;
   }
 }
 

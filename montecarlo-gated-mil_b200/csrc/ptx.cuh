@@ -186,6 +186,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// packed fp32x2 arithmetic (Blackwell FFMA2): two IEEE fp32 FMAs per instruction
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t r, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+
 __device__ __forceinline__ float tanh_approx(float x) {
   float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
