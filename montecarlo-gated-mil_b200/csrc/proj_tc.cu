@@ -13,7 +13,7 @@
 //          masked fp16 A slices (slot = K-slice, 64 KB/CTA, a full sample deep);
 //   regs : each producer thread keeps ITS 16 chunks of the fp16 feature tile in registers for the
 //          whole work item (converted from the fp32 features once per item);
-//   TMEM : two accumulator buffers (double buffered across t).
+//   TMEM : three accumulator buffers (sample t accumulates into buffer t % 3 while the epilogue drains t-1, t-2).
 // Warp roles (16 warps with 2 producer teams): 0-3 epilogue (TMEM -> tanh/sigmoid/gate/w-dot -> logits),
 //   4-11 producers (Philox mask -> masked fp16 A slice, generic-proxy st.shared + proxy fence),
 //   12-15 MMA issuers (sample tc is issued by warp 12 + tc % 4; 12 owns the TMEM allocation, 13 first
@@ -38,6 +38,11 @@ constexpr int TEAM_SLICES = NSLICE / TEAMS;      // slices per team and sample
 #endif
 constexpr int NMMA = MCMIL_MMA_WARPS;            // sample tc is issued by warp tc % NMMA into TMEM buffer tc & 1
 static_assert(NMMA == 2 || NMMA == 4, "MMA-issue warps: 2 or 4");
+#ifndef MCMIL_TMEM_BUFS
+#define MCMIL_TMEM_BUFS 3   // accumulator buffers in TMEM (3 x 160 of the 512 columns)
+#endif
+constexpr int NBUF = MCMIL_TMEM_BUFS;            // sample tc accumulates into buffer tc % NBUF
+static_assert(NBUF == 2 || (NBUF == 3 && NMMA == 4), "accumulator buffers: 2, or 3 with four issue warps");
 constexpr int PRODUCER_WARP0 = 4, MMA_WARP = PRODUCER_WARP0 + TEAMS * TEAM_WARPS, LOAD_WARP = MMA_WARP + 1;
 constexpr int TC_THREADS = (MMA_WARP + NMMA) * 32;
 
@@ -62,8 +67,8 @@ enum : int {
 enum : uint32_t {
   B_FULL = 0,                         // [NMMA][8] leader only: masked A slice of both CTAs is in smem (count 2 x TEAM_WARPS)
   B_EMPTY = B_FULL + NMMA * NSLICE,   // [NMMA][8] per CTA: the MMAs reading the slot have retired     (count 1)
-  B_TFULL = B_EMPTY + NMMA * NSLICE,  // [2] per CTA: accumulator buffer complete                      (count 1)
-  B_TEMPTY = B_TFULL + 2,             // [NMMA] leader only: both CTAs' epilogues drained the buffer   (count 8)
+  B_TFULL = B_EMPTY + NMMA * NSLICE,  // [NBUF] per CTA: accumulator buffer complete                   (count 1)
+  B_TEMPTY = B_TFULL + NBUF,          // [NMMA] leader only: both CTAs' epilogues drained the buffer   (count 8)
   B_WLOC = B_TEMPTY + NMMA,           // per CTA: W bulk copies landed                                 (tx)
   B_WREADY = B_WLOC + 1,              // leader only: both CTAs hold their W halves                    (count 2)
   B_COUNT = B_WREADY + 1,
@@ -77,6 +82,7 @@ static_assert(B_COUNT <= TMEM_SLOT && 8 * (TMEM_SLOT + 1) <= 1024, "barrier area
 //   [96,160) MMA "b" (N=128): 32 tanh | 32 sigmoid of hidden units 64..127
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_A = 0, TM_B = 96, TM_BUF_STRIDE = 160;
+static_assert(NBUF * TM_BUF_STRIDE <= TMEM_COLS, "TMEM columns");
 
 struct ProjParams {
   const float* H;          // [R][512] fp32 packed features
@@ -116,7 +122,7 @@ __device__ __forceinline__ uint32_t bar_addr(uint32_t sbase, uint32_t slot) { re
 #define MCMIL_RELAXED_NS_TEMPTY 256     // issue warps waiting for the accumulator buffer (idle ~2 samples out of 4)
 #endif
 #ifndef MCMIL_RELAXED_NS_TFULL
-#define MCMIL_RELAXED_NS_TFULL 128      // epilogue warps waiting for the next accumulator (double buffered)
+#define MCMIL_RELAXED_NS_TFULL 128      // epilogue warps waiting for the next accumulator (multi-buffered)
 #endif
 #ifdef MCMIL_EXP_WAITSTATS
 #define WAIT_T(acc, bar, parity) do { const long long w0_ = clock64(); mbar_wait(bar, parity); acc += clock64() - w0_; } while (0)
@@ -270,7 +276,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       mbar_init(bar_addr(sbase, B_FULL + s), 2 * TEAM_WARPS);
       mbar_init(bar_addr(sbase, B_EMPTY + s), 1);
     }
-    for (int b = 0; b < 2; ++b) mbar_init(bar_addr(sbase, B_TFULL + b), 1);
+    for (int b = 0; b < NBUF; ++b) mbar_init(bar_addr(sbase, B_TFULL + b), 1);
     for (int b = 0; b < NMMA; ++b) mbar_init(bar_addr(sbase, B_TEMPTY + b), 8);
     mbar_init(bar_addr(sbase, B_WLOC), 1);
     mbar_init(bar_addr(sbase, B_WREADY), 2);
@@ -321,13 +327,12 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       constexpr uint32_t IDESC_A = umma_idesc_f16(128, 2 * W_ROWS_A);
       constexpr uint32_t IDESC_B = umma_idesc_f16(128, 2 * W_ROWS_B);
       const uint32_t q = (uint32_t)(warp - MMA_WARP);          // this warp issues the samples tc = q (mod NMMA)
-      const uint32_t qb = q & 1u;                               // ... into TMEM accumulator buffer tc & 1
+      uint32_t mbuf = q % NBUF;                                 // ... into TMEM accumulator buffer tc % NBUF
       mbar_wait(bar_addr(sbase, B_WREADY), 0);
       tc_fence_after();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t adesc0 = umma_desc_sw128(sbase + SM_RING);
       const uint64_t bdesc0 = umma_desc_sw128(sbase + SM_W);
-      const uint32_t da = tmem_u + qb * TM_BUF_STRIDE + TM_A, db = tmem_u + qb * TM_BUF_STRIDE + TM_B;
       uint32_t j = 0;                                           // this warp's sample counter
       TRACE_DECL
 #ifdef MCMIL_EXP_PRODUCER_ONLY
@@ -335,15 +340,20 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 #endif
       for (long long u = u_begin + q; u < u_end; u += NMMA, ++j) {
         TRACE(NMMA * j + q, 0);
-        // buffer tc & 1 was last used by sample tc - 2, whose epilogue arrives on TEMPTY[(tc - 2) % NMMA]:
-        // that is phase j of TEMPTY[q - 2] for q >= 2, phase j - 1 of TEMPTY[q + NMMA - 2] otherwise
-        WAIT_R(wait_b, bar_addr(sbase, B_TEMPTY + ((q + NMMA - 2) & (NMMA - 1))), q >= 2 ? (j & 1) : ((j & 1) ^ 1), MCMIL_RELAXED_NS_TEMPTY);
+        // buffer tc % NBUF was last used by sample tc - NBUF, whose epilogue arrives on TEMPTY[(tc - NBUF) % NMMA]:
+        // that is phase j of TEMPTY[q - NBUF] for q >= NBUF, phase j - 1 of TEMPTY[q + NMMA - NBUF] otherwise
+        const uint32_t da = tmem_u + mbuf * TM_BUF_STRIDE + TM_A, db = tmem_u + mbuf * TM_BUF_STRIDE + TM_B;
+        WAIT_R(wait_b, bar_addr(sbase, B_TEMPTY + ((q + NMMA - NBUF) & (NMMA - 1))), q >= NBUF ? (j & 1) : ((j & 1) ^ 1), MCMIL_RELAXED_NS_TEMPTY);
         TRACE(NMMA * j + q, 1);
         tc_fence_after();
+        bool full_ready = false;                                // early probe of the next slice's FULL barrier
 #pragma unroll 1
         for (int s = 0; s < NSLICE; ++s) {
-          WAIT_T(wait_a, bar_addr(sbase, B_FULL + q * NSLICE + s), j & 1);
+          if (!full_ready) WAIT_T(wait_a, bar_addr(sbase, B_FULL + q * NSLICE + s), j & 1);
           tc_fence_after();
+#ifndef MCMIL_NO_EARLY_PROBE
+          full_ready = s + 1 < NSLICE && mbar_test_wait(bar_addr(sbase, B_FULL + q * NSLICE + s + 1), j & 1);
+#endif
           if (elect_one()) {
             // start-address field is (addr >> 4): advancing by bytes/16 stays inside the 14-bit field
             const uint64_t ad = adesc0 + (uint64_t)(s * (SLICE_BYTES_A >> 4));
@@ -369,8 +379,9 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
           __syncwarp();
           TRACE(NMMA * j + q, 2 + s);
         }
-        if (elect_one()) umma_commit_cg2_mc(bar_addr(sbase, B_TFULL + qb), 3);
+        if (elect_one()) umma_commit_cg2_mc(bar_addr(sbase, B_TFULL + mbuf), 3);
         __syncwarp();
+        mbuf = (mbuf + NMMA) % NBUF;
       }
       TRACE_DUMP("mma");
 #ifdef MCMIL_EXP_PRODUCER_ONLY
@@ -575,7 +586,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t tempty_leader = mapa(bar_addr(sbase, B_TEMPTY), 0);
     float* xch = reinterpret_cast<float*>(smem + SM_XCH);
-    uint32_t tc = 0;
+    uint32_t tc = 0, buf = 0, buf_phase = 0;      // accumulator buffer tc % NBUF and the parity of its use count
     TRACE_DECL
     grid_dep_wait();
 #ifdef MCMIL_EXP_PRODUCER_ONLY
@@ -592,9 +603,8 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       const bool valid = trow < td.nrows;
       const int g = td.row0 + trow;
       for (int t = t_begin; t < t_end; ++t, ++tc) {
-        const uint32_t buf = tc & 1;
         TRACE(tc, 0);
-        WAIT_R(wait_a, bar_addr(sbase, B_TFULL + buf), (tc >> 1) & 1, MCMIL_RELAXED_NS_TFULL);
+        WAIT_R(wait_a, bar_addr(sbase, B_TFULL + buf), buf_phase, MCMIL_RELAXED_NS_TFULL);
         TRACE(tc, 1);
         tc_fence_after();
         float acc[MAXC] = {0.f, 0.f, 0.f, 0.f};
@@ -618,6 +628,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(tempty_leader + (tc & (NMMA - 1)) * 8);
         TRACE(tc, 2);
+        if (++buf == NBUF) { buf = 0; buf_phase ^= 1; }
         // combine the two hidden-unit halves of each patch row.  The warps of the upper half also draw
         // the logit-dropout multipliers (one Philox call per row and sample), the warps of the lower half
         // do the global stores: the work left after the TMEM drain is split between the two warp pairs
