@@ -175,6 +175,8 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the ONE JSON line (NCCL prints its version banner there)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -188,6 +190,7 @@ def run_ours(args):
     S = 1 if shared else C
     w = mm.HeadWeights(make_state_dict(0, shared), dev)
     all_lens, T = workload(args.workload, args.bags_per_step, args.seed)
+    T_job = T
     t_offset, bag_ids = 0, None
     if args.workload == "config3" and world > 1:      # strong scaling: LPT bag sharding, no collective
         mine = MD.lpt_assign(all_lens, world)[rank]
@@ -215,7 +218,8 @@ def run_ours(args):
         r = mm.mc_head(w, H, T, seed=i, cu_seqlens=cu, bag_ids=bag_ids, t_offset=t_offset,
                        philox_rounds=rounds or args.philox_rounds)
         if args.workload == "config4" and world > 1:
-            _, _, merged_T[0] = MD.allreduce_welford([r.attn_mean, r.prob_mean], [r.attn_m2, r.prob_m2], T)
+            _, _, merged_T[0] = MD.allreduce_welford([r.attn_mean, r.prob_mean], [r.attn_m2, r.prob_m2], T,
+                                                     total_count=T_job)
         return r
 
     for i in range(max(args.warmup, 3)):

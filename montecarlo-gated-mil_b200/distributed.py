@@ -77,14 +77,17 @@ def welford_unpack(packed: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Te
     return mean, m2
 
 
-def allreduce_welford(means: Sequence[torch.Tensor], m2s: Sequence[torch.Tensor], count: int, group=None):
-    """ONE all-reduce for any number of statistic tensors. Returns (means, m2s, total_count)."""
+def allreduce_welford(means: Sequence[torch.Tensor], m2s: Sequence[torch.Tensor], count: int, group=None,
+                      total_count: Optional[int] = None):
+    """ONE all-reduce for any number of statistic tensors. Returns (means, m2s, total_count).
+    `total_count`: the merged sample count when the caller knows it (e.g. the job's T): the merged count is then
+    not read back from the device, so the call does not synchronise the host."""
     flat_mean = torch.cat([m.reshape(-1) for m in means])
     flat_m2 = torch.cat([m.reshape(-1) for m in m2s])
     packed = welford_pack(flat_mean, flat_m2, count)
     dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
     mean, m2 = welford_unpack(packed, flat_mean.numel())
-    total = int(round(float(packed[0].item())))
+    total = int(total_count) if total_count is not None else int(round(float(packed[0].item())))
     outs_mean, outs_m2, o = [], [], 0
     for m in means:
         outs_mean.append(mean[o:o + m.numel()].view_as(m))
@@ -104,7 +107,7 @@ def mc_head_sample_sharded(weights: HeadWeights, H: torch.Tensor, T_total: int, 
         raise ValueError("mc_head_sample_sharded: fewer MC samples than ranks")
     res = mc_head(weights, H, Tl, seed=seed, p_f=p_f, p_a=p_a, t_offset=t0, impl=impl)
     (am, pm), (aq, pq), total = allreduce_welford([res.attn_mean, res.prob_mean], [res.attn_m2, res.prob_m2],
-                                                   Tl, group)
+                                                   Tl, group, total_count=T_total)
     Y = res.Y
     if gather_Y:  # only callers that want medians / IQR of the per-sample probabilities (infer.py:50-55)
         sizes = [mc_shard(T_total, r, world)[1] for r in range(world)]
