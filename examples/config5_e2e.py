@@ -37,12 +37,14 @@ def main():
     ap.add_argument("--T", type=int, default=100)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--separate", action="store_true")
+    ap.add_argument("--extractor-mode", default="channels_last", choices=["eager", "channels_last", "graph"])
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     model = mm.MultiHeadGatedAttentionMIL(pretrained=False, shared_attention=not args.separate)
     model.apply(mm.deactivate_batchnorm)                      # infer.py:105-109,154
     model.to(dev).eval()
+    model.extractor_mode = args.extractor_mode                # torch extractor, channels-last + CUDA graph
     patcher = mm.ImagePatcher(patch_size=224, overlap=args.overlap, bag_size=-1, empty_thresh=0.75)
     patcher.get_tiles(args.height, args.width)
     img = synth_mammogram(0, args.height, args.width, dev)
@@ -72,7 +74,7 @@ def main():
     t = np.array(times).mean(0)
     probs = res.probs()[0]
     out = {"workload": f"config5: {args.height}x{args.width} image, overlap {args.overlap}, {len(idx)} of {len(patcher.tiles)} tiles, "
-                       f"ResNet-18 (batch-stat BN), T={args.T}",
+                       f"ResNet-18 (batch-stat BN, extractor_mode={args.extractor_mode}), T={args.T}",
            "ms": {"tiling_and_bag": t[0], "resnet18_features": t[1], "mc_head": t[2], "attention_map_stats": t[3],
                   "total": float(t.sum())},
            "prob_mean": res.prob_mean[0].tolist(), "prob_std": res.prob_var(0)[0].sqrt().tolist(),

@@ -404,6 +404,8 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     const uint32_t empty_team = pin(bar_addr(sbase, B_EMPTY) + (uint32_t)team * 8u);
     const uint32_t thr2 = pin(P.thr_f | (P.thr_f << 16));
     const int chunk = lane & 7;
+    const uint32_t q0 = pin((uint32_t)(team * 8 + chunk));       // Philox chunk index of this thread in slice `team`
+    const uint32_t lane0 = pin(lane == 0 ? 1u : 0u);
     int rowi[4]; uint32_t off[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -452,9 +454,9 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       uint4 ref = make_uint4(0, 0, 0, 0);                                // word i: row slot i, byte si: this team's si-th slice
       if constexpr (DRAW) {
         const uint32_t tg0 = (uint32_t)(P.t_offset + t_begin);
-        ref = philox4x32<ROUNDS>(REF_CHUNK_BASE + (uint32_t)(team * 8 + chunk), nrow[0], tg0, bag, P.key);
-        rnd[0] = philox4x32<ROUNDS>((uint32_t)(team * 8 + chunk), nrow[0], tg0, bag, P.key);
-        rnd[1] = philox4x32<ROUNDS>((uint32_t)(team * 8 + chunk), nrow[2], tg0, bag, P.key);
+        ref = philox4x32<ROUNDS>(REF_CHUNK_BASE + q0, nrow[0], tg0, bag, P.key);
+        rnd[0] = philox4x32<ROUNDS>(q0, nrow[0], tg0, bag, P.key);
+        rnd[1] = philox4x32<ROUNDS>(q0, nrow[2], tg0, bag, P.key);
       }
       // mask cache (separate attention): one 64-byte record per (sample, packed row), byte
       // [chunk][team][si] = keep bits of chunk (TEAMS*si+team)*8+chunk; a thread owns one 32-bit word
@@ -503,7 +505,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 #endif
 #ifdef MCMIL_EXP_MMA_ONLY       // experiment: no producer work at all, the MMA / epilogue chain runs flat out
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(full_team + (full_set + TEAMS * si) * 8);
+          if (lane0) mbar_arrive_cluster(full_team + (full_set + TEAMS * si) * 8);
           continue;
 #endif
           uint4 nxt[2], ref_nxt = ref;
@@ -552,17 +554,17 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 #endif
           if constexpr (DRAW) {
             // next slice of this team: (s + TEAMS, t), or (team, t + 1) after the last one of the sample
-            const uint32_t q_next = (uint32_t)((si < TEAM_SLICES - 1 ? s + TEAMS : team) * 8 + chunk);
+            const uint32_t q_next = q0 + (uint32_t)(si < TEAM_SLICES - 1 ? TEAMS * (si + 1) * 8 : 0);
             const uint32_t t_next = si < TEAM_SLICES - 1 ? tg : tg + 1u;
             nxt[0] = philox4x32<ROUNDS>(q_next, nrow[0], t_next, bag, P.key);
             nxt[1] = philox4x32<ROUNDS>(q_next, nrow[2], t_next, bag, P.key);
             if (si == TEAM_SLICES - 1)
-              ref_nxt = philox4x32<ROUNDS>(REF_CHUNK_BASE + (uint32_t)(team * 8 + chunk), nrow[0], t_next, bag, P.key);
+              ref_nxt = philox4x32<ROUNDS>(REF_CHUNK_BASE + q0, nrow[0], t_next, bag, P.key);
           }
           TRACE(tc, 4 * si + 2);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(full_team + (full_set + TEAMS * si) * 8);
+          if (lane0) mbar_arrive_cluster(full_team + (full_set + TEAMS * si) * 8);
           TRACE(tc, 4 * si + 3);
           if constexpr (DRAW) { rnd[0] = nxt[0]; rnd[1] = nxt[1]; ref = ref_nxt; }
         }

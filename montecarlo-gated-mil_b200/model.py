@@ -31,6 +31,51 @@ def _make_backbone(backbone: str, pretrained: bool):
     return ctor[backbone](weights=weights)
 
 
+class _ExtractorRunner:
+    """SURVEY.md §8f-4.  The ResNet extractor stays in PyTorch (north_star); this runner only changes HOW torch
+    runs it: channels-last activations / weights and, in "graph" mode, one CUDA graph per bag shape, so a bag
+    costs one graph launch instead of ~120 kernel launches.  BatchNorm keeps the reference's whole-bag batch
+    statistics (`deactivate_batchnorm`: the bag is ONE batch inside the graph), results are the eager ones up
+    to cuDNN's algorithm choice."""
+
+    def __init__(self):
+        self.graphs = {}          # (shape, device) -> (graph, static_in, static_out)
+
+    def run(self, module: nn.Module, x: torch.Tensor, mode: str) -> torch.Tensor:
+        if mode == "eager":
+            return module(x)
+        if mode not in ("channels_last", "graph"):
+            raise ValueError(f"extractor_mode must be eager / channels_last / graph, got {mode!r}")
+        if x.device.type != "cuda":
+            raise RuntimeError("extractor_mode channels_last / graph need CUDA tensors")
+        if next(module.parameters()).dim() and not getattr(module, "_mcmil_cl", False):
+            module.to(memory_format=torch.channels_last)
+            module._mcmil_cl = True
+        x = x.contiguous(memory_format=torch.channels_last)
+        if mode == "channels_last":
+            return module(x)
+        key = (tuple(x.shape), str(x.device))
+        ent = self.graphs.get(key)
+        if ent is None:
+            if len(self.graphs) >= 8:
+                self.graphs.clear()
+            static_in = x.clone(memory_format=torch.channels_last)
+            side = torch.cuda.Stream(x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(2):
+                    module(static_in)                       # warm-up: cuDNN algorithm selection, workspaces
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g), torch.no_grad():
+                static_out = module(static_in)
+            ent = self.graphs[key] = (g, static_in, static_out)
+        g, static_in, static_out = ent
+        static_in.copy_(x)
+        g.replay()
+        return static_out.clone()
+
+
 class MultiHeadGatedAttentionMIL(nn.Module):
     def __init__(self, num_classes=2, backbone="r18", pretrained=True, L=512, D=128,
                  feature_dropout=0.1, attention_dropout=0.1, shared_attention=True, neptune_run=None):
@@ -58,6 +103,8 @@ class MultiHeadGatedAttentionMIL(nn.Module):
         self.mc_seed = 0             # Philox key of the next mc_inference call (auto-incremented)
         self.last_result: MCHeadResult | None = None
         self.fused_eval = True       # eval-mode forward() through the fused head (forward_eval_fused)
+        self.extractor_mode = "eager"  # "channels_last" / "graph": how torch runs the extractor for mc_inference
+        self._extractor_runner = _ExtractorRunner()
 
     # ------------------------------------------------------------------ forward (model.py:211-253)
     AUX_MARGIN, AUX_SCALE = 1.0, 0.5          # AuxiliaryLoss(loss_type='pairwise', margin=1.0, scale=.5), model.py:149-151
@@ -123,7 +170,9 @@ class MultiHeadGatedAttentionMIL(nn.Module):
         bs, n = input_tensor.shape[:2]
         if bs != 1:
             raise RuntimeError("mc_inference supports bs == 1 only (as the reference, model.py:309)")
-        H = self.feature_extractor(input_tensor.view(-1, *input_tensor.shape[-3:]))
+        x = input_tensor.view(-1, *input_tensor.shape[-3:])
+        mode = self.extractor_mode if (x.is_cuda and x.dim() == 4 and not torch.is_grad_enabled()) else "eager"
+        H = self._extractor_runner.run(self.feature_extractor, x, mode)
         return H.view(n, -1).float().contiguous()
 
     def mc_inference_stats(self, input_tensor, N=30, device="cuda", seed=None, return_attention=False,

@@ -316,6 +316,28 @@ def test_module_forward_eval_fused_matches_torch_path(mm):
         assert m(x)[0].requires_grad                  # training keeps the torch graph
 
 
+def test_extractor_modes_agree(mm):
+    """channels-last / CUDA-graph execution of the torch extractor (whole-bag batch-stat BN kept)
+    gives the eager features; the graph is reused across bags of the same shape."""
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    m = mm.MultiHeadGatedAttentionMIL(pretrained=False)
+    m.apply(mm.deactivate_batchnorm)
+    m.to(dev).eval()
+    bags = [torch.rand(1, 12, 3, 224, 224, device=dev) for _ in range(2)]
+    with torch.no_grad():
+        ref = [m.extract_features(b) for b in bags]
+        for mode in ("channels_last", "graph"):
+            m.extractor_mode = mode
+            for b, r in zip(bags, ref):
+                H = m.extract_features(b)
+                assert H.shape == r.shape == (12, 512)
+                assert (H - r).abs().max() < 2e-3 * max(1.0, float(r.abs().max())), mode
+        assert len(m._extractor_runner.graphs) == 1
+        Y, A = m.mc_inference(bags[0], N=4, device="cuda", seed=1)
+        assert Y.shape == (4, 1, 2) and A.shape == (4, 1, 2, 12)
+
+
 def test_argument_errors(mm):
     dev = torch.device("cuda")
     sd = G.make_weights(1, 2, True)
