@@ -47,10 +47,19 @@ constexpr int PRODUCER_WARP0 = 4, MMA_WARP = PRODUCER_WARP0 + TEAMS * TEAM_WARPS
 constexpr int TC_THREADS = (MMA_WARP + NMMA) * 32;
 
 constexpr uint32_t SM_W = 0;
-constexpr uint32_t SM_RING = SM_W + NSLICE * SLICE_BYTES_W;        // 139264: 8 slots x 8 KB
-constexpr uint32_t SM_XCH = SM_RING + NSLICE * SLICE_BYTES_A;      // 204800: [2][64][2 x 4] floats (partial sums | logit multipliers)
-constexpr uint32_t SM_BAR = SM_XCH + 2 * HALF_ROWS * 2 * MAXC * 4; // 208896
-constexpr uint32_t SM_TOTAL = SM_BAR + 1024;                       // 209920 <= 232448 (227 KB)
+constexpr uint32_t SM_RING = SM_W + NSLICE * SLICE_BYTES_W;        // 139264: RING_SLOTS x 8 KB
+#ifndef MCMIL_RING_EXTRA
+#define MCMIL_RING_EXTRA 0   // extra ring slots per producer team beyond one sample (1 = the 2 x 8 KB of smem left over;
+                             // measured: no gain once the producers stopped waiting, profiles/r1_experiments.md)
+#endif
+constexpr int RING_EXTRA = MCMIL_RING_EXTRA;
+constexpr int TEAM_SLOTS = TEAM_SLICES + RING_EXTRA;       // ring slots owned by one team; its j-th slice uses slot j % TEAM_SLOTS
+constexpr int RING_SLOTS = TEAMS * TEAM_SLOTS;             // slot index = TEAMS * (j % TEAM_SLOTS) + team
+static_assert(RING_EXTRA == 0 || RING_EXTRA == 1, "ring depth: one sample, or one sample + one slice per team");
+constexpr uint32_t SM_XCH = SM_RING + RING_SLOTS * SLICE_BYTES_A;  // [2][64][2 x 4] floats (partial sums | logit multipliers)
+constexpr uint32_t SM_BAR = SM_XCH + 2 * HALF_ROWS * 2 * MAXC * 4;
+constexpr uint32_t SM_TOTAL = SM_BAR + 1024;                       // 209920 (226304 with the 10-slot ring)
+static_assert(SM_TOTAL <= 232448, "227 KB of dynamic shared memory per CTA");
 
 // where the feature keep-masks come from
 enum : int {
@@ -328,6 +337,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       constexpr uint32_t IDESC_B = umma_idesc_f16(128, 2 * W_ROWS_B);
       const uint32_t q = (uint32_t)(warp - MMA_WARP);          // this warp issues the samples tc = q (mod NMMA)
       uint32_t mbuf = q % NBUF;                                 // ... into TMEM accumulator buffer tc % NBUF
+      uint32_t mslot = (q * TEAM_SLICES) % TEAM_SLOTS;          // ring slot (per team) of the sample's first slice
       mbar_wait(bar_addr(sbase, B_WREADY), 0);
       tc_fence_after();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -356,7 +366,9 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 #endif
           if (elect_one()) {
             // start-address field is (addr >> 4): advancing by bytes/16 stays inside the 14-bit field
-            const uint64_t ad = adesc0 + (uint64_t)(s * (SLICE_BYTES_A >> 4));
+            uint32_t m = mslot + (uint32_t)(s / TEAMS);
+            if (m >= TEAM_SLOTS) m -= TEAM_SLOTS;
+            const uint64_t ad = adesc0 + (uint64_t)((m * TEAMS + (uint32_t)(s % TEAMS)) * (SLICE_BYTES_A >> 4));
             const uint64_t bd = bdesc0 + (uint64_t)(s * (SLICE_BYTES_W >> 4));
 #if defined(MCMIL_EXP_MMA_ORDER)
 #pragma unroll
@@ -382,6 +394,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         if (elect_one()) umma_commit_cg2_mc(bar_addr(sbase, B_TFULL + mbuf), 3);
         __syncwarp();
         mbuf = (mbuf + NMMA) % NBUF;
+        mslot = (mslot + NMMA * TEAM_SLICES) % TEAM_SLOTS;
       }
       TRACE_DUMP("mma");
 #ifdef MCMIL_EXP_PRODUCER_ONLY
@@ -415,6 +428,18 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     }
     uint32_t tc = 0;                                  // samples processed so far by this pair
     bool slot_free = false;                           // early probe result for the next ring slot
+    uint32_t pslot = 0;                               // ring slot (within this team's TEAM_SLOTS) of the next slice
+    // The slot of this team's slice (tc, si) was last used by its slice RING_EXTRA earlier than (tc-1, si):
+    // its EMPTY barrier belongs to the issue warp of that sample.
+    auto empty_of = [&](uint32_t tcv, int siv, uint32_t& bar, uint32_t& parity) -> bool {
+      constexpr uint32_t LOGM_ = NMMA == 4 ? 2 : 1;
+      uint32_t tp = tcv - 1u;
+      int sp = siv - RING_EXTRA;
+      if (sp < 0) { sp += TEAM_SLICES; tp -= 1u; }
+      bar = empty_team + ((tp & (NMMA - 1)) * NSLICE + TEAMS * sp) * 8;
+      parity = (tp >> LOGM_) & 1u;
+      return (int32_t)tp >= 0 && tcv != 0u;
+    };
     TRACE_DECL
     grid_dep_wait();
     for (long long u = u_begin; u < u_end;) {
@@ -480,8 +505,6 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       for (int t = t_begin; t < t_end; ++t, ++tc) {
         const uint32_t tg = (uint32_t)(P.t_offset + t);
         // slot s was last read by the MMAs of sample tc-1, issued by warp (tc-1)&1 as its ((tc-1)>>1)-th
-        constexpr uint32_t LOGM = NMMA == 4 ? 2 : 1;
-        const uint32_t empty_set = ((tc - 1) & (NMMA - 1)) * NSLICE, empty_parity = ((tc - 1) >> LOGM) & 1;
         const uint32_t full_set = (tc & (NMMA - 1)) * NSLICE;
         uint32_t cnext[4] = {0u, 0u, 0u, 0u};
         if constexpr (MASK == MASK_CACHED) {                   // prefetch the next sample's keep bytes
@@ -496,13 +519,19 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
           const int s = TEAMS * si + team;
 #ifndef MCMIL_EXP_PRODUCER_ONLY
           TRACE(tc, 4 * si);
+          {
+            uint32_t ebar, epar;
+            const bool used = empty_of(tc, si, ebar, epar);
 #ifndef MCMIL_NO_EARLY_PROBE
-          if (tc > 0 && !slot_free) WAIT_T(wait_a, empty_team + (empty_set + TEAMS * si) * 8, empty_parity);
+            if (used && !slot_free) WAIT_T(wait_a, ebar, epar);
 #else
-          if (tc > 0) WAIT_T(wait_a, empty_team + (empty_set + TEAMS * si) * 8, empty_parity);
+            if (used) WAIT_T(wait_a, ebar, epar);
 #endif
+          }
           TRACE(tc, 4 * si + 1);
 #endif
+          const uint32_t slot_off = pslot * (uint32_t)(TEAMS * SLICE_BYTES_A);
+          pslot = pslot + 1 == TEAM_SLOTS ? 0u : pslot + 1;
 #ifdef MCMIL_EXP_MMA_ONLY       // experiment: no producer work at all, the MMA / epilogue chain runs flat out
           __syncwarp();
           if (lane0) mbar_arrive_cluster(full_team + (full_set + TEAMS * si) * 8);
@@ -538,7 +567,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
               m.z = (bits & 16u ? 0x0000FFFFu : 0u) | (bits & 32u ? 0xFFFF0000u : 0u);
               m.w = (bits & 64u ? 0x0000FFFFu : 0u) | (bits & 128u ? 0xFFFF0000u : 0u);
             }
-            sts128(off[i] + (uint32_t)(TEAMS * si) * SLICE_BYTES_A, make_uint4(h.x & m.x, h.y & m.y, h.z & m.z, h.w & m.w));
+            sts128(off[i] + slot_off, make_uint4(h.x & m.x, h.y & m.y, h.z & m.z, h.w & m.w));
           }
 #if !defined(MCMIL_NO_EARLY_PROBE) && !defined(MCMIL_EXP_PRODUCER_ONLY)
           // Probe the barrier of the NEXT slot now: the answer (an ~200-cycle round trip through the
@@ -546,10 +575,9 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
           // block below; the blocking wait above is only entered when the slot is really still in use.
           {
             const bool last = si == TEAM_SLICES - 1;
-            const uint32_t nset = last ? full_set : empty_set;                       // empty_set of sample tc+1 == full_set of tc
-            const uint32_t npar = last ? ((tc >> LOGM) & 1) : empty_parity;
-            const int nsi = last ? 0 : si + 1;
-            slot_free = (last || tc > 0) && mbar_test_wait(empty_team + (nset + TEAMS * nsi) * 8, npar);
+            uint32_t nbar, npar;
+            const bool used = empty_of(last ? tc + 1u : tc, last ? 0 : si + 1, nbar, npar);
+            slot_free = used && mbar_test_wait(nbar, npar);
           }
 #endif
           if constexpr (DRAW) {
@@ -631,34 +659,39 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         if (lane == 0) mbar_arrive_cluster(tempty_leader + (tc & (NMMA - 1)) * 8);
         TRACE(tc, 2);
         if (++buf == NBUF) { buf = 0; buf_phase ^= 1; }
-        // combine the two hidden-unit halves of each patch row.  The warps of the upper half also draw
-        // the logit-dropout multipliers (one Philox call per row and sample), the warps of the lower half
-        // do the global stores: the work left after the TMEM drain is split between the two warp pairs
-        // (= between SM sub-partitions 0,1 and 2,3, which all host two producer warps).
+        // combine the two hidden-unit halves of each patch row.  The lower-half warps do the global stores;
+        // the logit-dropout multipliers (one Philox call per row and sample) are drawn by the upper-half
+        // warps on even samples and by the lower-half warps on odd ones: the work left after the TMEM drain
+        // is split between the two warp pairs (= SM sub-partitions 0,1 and 2,3, which all host two producers).
         float* x = xch + ((tc & 1) * HALF_ROWS + r) * (2 * MAXC);
-        if (half == 1) {
-          float mult[MAXC] = {0.f, 0.f, 0.f, 0.f};
-          if (valid) {
-            const uint32_t tg = (uint32_t)(P.t_offset + t);
-            uint4 rnd = make_uint4(0, 0, 0, 0);
-            if constexpr (!INJECT)
-              rnd = attn_words<ROUNDS>(0u, (uint32_t)(td.n0 + trow), tg, (uint32_t)(P.bag_offset + td.gbag), P.key);
+        const bool draws = (half == 1) == ((tc & 1) == 0);
+        float mult[MAXC] = {0.f, 0.f, 0.f, 0.f};
+        if (draws && valid) {
+          const uint32_t tg = (uint32_t)(P.t_offset + t);
+          uint4 rnd = make_uint4(0, 0, 0, 0);
+          if constexpr (!INJECT)
+            rnd = attn_words<ROUNDS>(0u, (uint32_t)(td.n0 + trow), tg, (uint32_t)(P.bag_offset + td.gbag), P.key);
 #pragma unroll
-            for (int c = 0; c < NOUT; ++c) {
-              const int head = P.head0 + c;
-              bool keep;
-              if constexpr (!INJECT) keep = attn_keep_from(rnd, head, P.thr_a);
-              else keep = (P.inj_attn[((size_t)t * P.C + head) * (P.Rp >> 5) + (g >> 5)] >> (g & 31)) & 1u;
-              mult[c] = keep ? P.sa : 0.f;
-            }
+          for (int c = 0; c < NOUT; ++c) {
+            const int head = P.head0 + c;
+            bool keep;
+            if constexpr (!INJECT) keep = attn_keep_from(rnd, head, P.thr_a);
+            else keep = (P.inj_attn[((size_t)t * P.C + head) * (P.Rp >> 5) + (g >> 5)] >> (g & 31)) & 1u;
+            mult[c] = keep ? P.sa : 0.f;
           }
+        }
+        if (half == 1) {
           *reinterpret_cast<float4*>(x) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-          *reinterpret_cast<float4*>(x + MAXC) = make_float4(mult[0], mult[1], mult[2], mult[3]);
+          if (draws) *reinterpret_cast<float4*>(x + MAXC) = make_float4(mult[0], mult[1], mult[2], mult[3]);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (half == 0 && valid) {
-          const float4 xs = *reinterpret_cast<const float4*>(x), xm = *reinterpret_cast<const float4*>(x + MAXC);
-          const float part[MAXC] = {xs.x, xs.y, xs.z, xs.w}, mult[MAXC] = {xm.x, xm.y, xm.z, xm.w};
+          const float4 xs = *reinterpret_cast<const float4*>(x);
+          const float part[MAXC] = {xs.x, xs.y, xs.z, xs.w};
+          if (!draws) {
+            const float4 xm = *reinterpret_cast<const float4*>(x + MAXC);
+            mult[0] = xm.x; mult[1] = xm.y; mult[2] = xm.z; mult[3] = xm.w;
+          }
 #pragma unroll
           for (int c = 0; c < NOUT; ++c) {
             const int head = P.head0 + c;
