@@ -263,6 +263,17 @@ def run_ours(args):
                 "frac": achieved / peak, "peak_source": "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback",
                 "frac_of_sustained": achieved / peak_sust, "kernel_ms": k_ms, "kernel_launches": prof_k.value,
                 "kernel_share_of_step": prof_ms.value / ms_total if ms_total > 0 else None, "traffic": None}
+    # DRAM traffic per launch of that kernel, from the committed ncu capture of this very configuration
+    # (profiles/r1_traffic.json; ncu is never attached to a timed run)
+    if args.workload == "config2" and args.bags_per_step == 256 and shared and args.philox_rounds == 10:
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tr = json.load(f)["config2_shared"]
+            roofline["traffic"] = tr["dram_read_bytes"] + tr["dram_write_bytes"]
+            roofline["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json)"
+            roofline["algorithmic_bytes"] = sum(tr["algorithmic_bytes"].values())
+        except Exception:  # noqa: BLE001
+            pass
 
     # ---- the same step with Philox4x32-7 masks (optional fast mode; not the headline)
     philox7 = None
