@@ -756,9 +756,14 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
     attr_set = true;
   }
   if (dbg != nullptr && !(w.shared && w.C == 2 && m.inj_feat == nullptr && m.rounds == 10)) return cudaErrorInvalidValue;
-  int dev = 0, sms = 0;
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sms_of[64] = {0};                       // SM count per device ordinal (queried once)
+  int sms = dev >= 0 && dev < 64 ? sms_of[dev] : 0;
+  if (sms == 0) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (dev >= 0 && dev < 64) sms_of[dev] = sms;
+  }
   const long long units = (long long)p.n_tiles * p.T;
   int n_pairs = sms / 2;
   if (units < n_pairs) n_pairs = (int)units;

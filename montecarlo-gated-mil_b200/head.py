@@ -246,6 +246,46 @@ def mc_head(weights: HeadWeights, H: torch.Tensor, T: int, seed: int = 0,
     return MCHeadResult(Y, pm, pq, am, aq, A, T, cu, launches)
 
 
+class MCHeadRunner:
+    """Low-overhead repeated calls for ONE fixed shape (the reference's bs == 1 serving loop, infer.py:187-196):
+    plan, workspace and output tensors are created once, `run(H, seed)` is a single C-ABI call (no allocation,
+    no validation beyond the shape).  The returned MCHeadResult aliases the runner's buffers: it is valid until
+    the next `run`.  Same kernels and results as `mc_head`."""
+
+    def __init__(self, weights: HeadWeights, n_rows: int, T: int, p_f: float = 0.1, p_a: float = 0.1,
+                 cu_seqlens: Optional[Sequence[int]] = None, return_attention: bool = False,
+                 philox_rounds: int = 10, impl: str = "tcgen05"):
+        self.lib = _lib.load()
+        self.w, self.dev, self.T, self.R = weights, weights.device, int(T), int(n_rows)
+        cu = np.array([0, n_rows], np.int32) if cu_seqlens is None else np.asarray(cu_seqlens, dtype=np.int32)
+        if cu[0] != 0 or cu[-1] != n_rows or np.any(np.diff(cu) <= 0) or T < 1:
+            raise ValueError("MCHeadRunner: bad cu_seqlens / T")
+        C_ = weights.num_classes
+        self.plan = _get_plan(cu, T, C_, self.dev)
+        nb = self.plan.n_bags
+        with torch.cuda.device(self.dev):
+            f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.dev)   # noqa: E731
+            self.Y, self.pm, self.pq = f(nb, T, C_), f(nb, C_), f(nb, C_)
+            self.am, self.aq = f(C_, n_rows), f(C_, n_rows)
+            self.A = f(T, C_, n_rows) if return_attention else None
+            self.ws = torch.empty(self.plan.ws_bytes + 2048, dtype=torch.uint8, device=self.dev)
+        off = (-self.ws.data_ptr()) % 1024
+        self._tail = (int(philox_rounds), float(p_f), float(p_a), None, None, _lib.IMPLS[impl],
+                      _ptr(self.Y), _ptr(self.A), _ptr(self.pm), _ptr(self.pq), _ptr(self.am), _ptr(self.aq),
+                      C.c_void_p(self.ws.data_ptr() + off), self.plan.ws_bytes)
+        self.result = MCHeadResult(self.Y, self.pm, self.pq, self.am, self.aq, self.A, self.T, cu, 0)
+
+    def run(self, H: torch.Tensor, seed: int = 0, t_offset: int = 0, bag_offset: int = 0) -> MCHeadResult:
+        if H.device != self.dev or H.dtype != torch.float32 or tuple(H.shape) != (self.R, L_FEAT) or not H.is_contiguous():
+            raise ValueError(f"MCHeadRunner.run: H must be a contiguous float32 ({self.R}, {L_FEAT}) tensor on {self.dev}")
+        code = self.lib.mcmil_head_forward(self.w._h, self.plan._h, C.c_void_p(H.data_ptr()), int(t_offset),
+                                           int(bag_offset), int(seed) & 0xFFFFFFFFFFFFFFFF, *self._tail,
+                                           C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream))
+        if code:
+            _lib.check(code, "mcmil_head_forward")
+        return self.result
+
+
 def head_forward_eval(weights: HeadWeights, H: torch.Tensor, cu_seqlens: Optional[Sequence[int]] = None):
     """Deterministic (eval-mode) forward of the head, /root/reference/model.py:216-240 with the dropout
     modules inactive: one pass of the same fused kernels with every mask element kept.

@@ -316,6 +316,22 @@ def test_module_forward_eval_fused_matches_torch_path(mm):
         assert m(x)[0].requires_grad                  # training keeps the torch graph
 
 
+def test_runner_equals_mc_head(mm):
+    """MCHeadRunner (pre-created plan / outputs, one C-ABI call per bag) returns bit-identical results."""
+    dev = torch.device("cuda")
+    sd = G.make_weights(5, 2, True)
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
+    r = mm.MCHeadRunner(w, 300, 7, return_attention=True)
+    for seed in (1, 2):
+        H = torch.from_numpy(G.make_features(40 + seed, 300)).to(dev)
+        a = r.run(H, seed=seed)
+        b = mm.mc_head(w, H, 7, seed=seed, return_attention=True)
+        for x, y in ((a.Y, b.Y), (a.A, b.A), (a.attn_mean, b.attn_mean), (a.attn_m2, b.attn_m2), (a.prob_mean, b.prob_mean)):
+            assert torch.equal(x, y)
+    with pytest.raises(ValueError):
+        r.run(torch.zeros(10, 512, device=dev))
+
+
 def test_extractor_modes_agree(mm):
     """channels-last / CUDA-graph execution of the torch extractor (whole-bag batch-stat BN kept)
     gives the eager features; the graph is reused across bags of the same shape."""
