@@ -28,7 +28,7 @@ namespace mcmil {
 using namespace ptx;
 
 #ifndef MCMIL_TEAMS
-#define MCMIL_TEAMS 2   // 4 (16 producer warps, 80 regs/thread, small spills) measured within 2 %: profiles/r1_experiments.md
+#define MCMIL_TEAMS 2   // the mask / cache indexing of the Philox modes assumes 2 (static_asserts below)
 #endif
 constexpr int TEAMS = MCMIL_TEAMS;               // producer teams: team k fills the K-slices s = k (mod TEAMS)
 constexpr int TEAM_WARPS = 4;                    // warps per team (16 patch rows each)
@@ -36,7 +36,7 @@ constexpr int TEAM_SLICES = NSLICE / TEAMS;      // slices per team and sample
 #ifndef MCMIL_MMA_WARPS
 #define MCMIL_MMA_WARPS 4   // MMA-issue warps, one per SM sub-partition of the leader CTA (see the role comment below)
 #endif
-constexpr int NMMA = MCMIL_MMA_WARPS;            // sample tc is issued by warp tc % NMMA into TMEM buffer tc & 1
+constexpr int NMMA = MCMIL_MMA_WARPS;            // sample tc is issued by warp tc % NMMA
 static_assert(NMMA == 2 || NMMA == 4, "MMA-issue warps: 2 or 4");
 #ifndef MCMIL_TMEM_BUFS
 #define MCMIL_TMEM_BUFS 3   // accumulator buffers in TMEM (3 x 160 of the 512 columns)

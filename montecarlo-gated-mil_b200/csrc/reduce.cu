@@ -65,14 +65,16 @@ softmax_rows_kernel(const float* __restrict__ logits, const float* __restrict__ 
   }
 }
 
-constexpr int COL_LANES = 32;     // packed rows (patches) per CTA
+constexpr int COL_LANES = 32;
+constexpr int COL_VEC = 4;        // packed rows (patches) per lane: one 16-byte load per sample
+constexpr int COL_COLS = COL_LANES * COL_VEC;   // packed rows per CTA
 constexpr int COL_TGROUPS = 8;    // MC samples are strided over 8 warps, then merged in a fixed order
 constexpr int COL_THREADS = COL_LANES * COL_TGROUPS;
 
-// grid.x < col_blocks: CTA = 32 packed rows x one head; warp g runs Welford over the samples
-//   t = g, g+8, ... of A[t,c,row] (coalesced along the patch axis, 8 independent chains per row),
-//   then the 8 partial (count, mean, M2) are merged with Chan's formula in warp order 0..7
-//   (deterministic).  Optionally stores A.
+// grid.x < col_blocks: CTA = 128 packed rows x one head; warp g runs Welford over the samples
+//   t = g, g+8, ... of A[t,c,row], each lane on 4 adjacent rows (one float4 of the logit plane per sample:
+//   512 B per warp and load, 8 independent warps per CTA), then the 8 partial (count, mean, M2) per row are
+//   merged with Chan's formula in warp order 0..7 (deterministic).  Optionally stores A.
 // grid.x >= col_blocks: one warp per bag: mean / M2 over t of softmax_c(Y[bag][t][:])
 __global__ void __launch_bounds__(COL_THREADS)
 welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__ rowstat,
@@ -84,40 +86,57 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
   asm volatile("griddepcontrol.wait;" ::: "memory");         // rowstat / Y of softmax_rows_kernel
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if ((int)blockIdx.x < col_blocks) {
-    __shared__ float s_mean[COL_TGROUPS][COL_LANES], s_m2[COL_TGROUPS][COL_LANES];
+    __shared__ float s_mean[COL_TGROUPS][COL_COLS], s_m2[COL_TGROUPS][COL_COLS];
     const int c = blockIdx.y;
-    const int g = blockIdx.x * COL_LANES + lane;
-    float mean = 0.f, m2 = 0.f;
+    const int g0 = blockIdx.x * COL_COLS + lane * COL_VEC;   // multiple of 4; the planes have stride Rp (multiple of 32)
+    float mean[COL_VEC] = {0.f, 0.f, 0.f, 0.f}, m2[COL_VEC] = {0.f, 0.f, 0.f, 0.f};
     int cnt = 0;
-    if (g < R) {
-      const int b = row2bag[g];
+    if (g0 < R) {
+      int b[COL_VEC];
+#pragma unroll
+      for (int k = 0; k < COL_VEC; ++k) b[k] = row2bag[min(g0 + k, R - 1)];
+      const bool one_bag = b[0] == b[COL_VEC - 1];
 #pragma unroll 4
       for (int t = grp; t < T; t += COL_TGROUPS) {
-        const float2 rs = __ldg(rowstat + ((size_t)t * C + c) * n_bags + b);
-        const float a = __expf(__ldg(logits + ((size_t)t * C + c) * Rp + g) - rs.x) * rs.y;
-        if (A) A[((size_t)t * C + c) * R + g] = a;
+        const size_t plane = (size_t)t * C + c;
+        // rows >= R of the last float4 are padding of the plane (never written, never used below)
+        const float4 l4 = __ldg(reinterpret_cast<const float4*>(logits + plane * Rp + g0));
+        const float lg[COL_VEC] = {l4.x, l4.y, l4.z, l4.w};
+        float2 rs[COL_VEC];
+        rs[0] = __ldg(rowstat + plane * n_bags + b[0]);
+#pragma unroll
+        for (int k = 1; k < COL_VEC; ++k) rs[k] = one_bag ? rs[0] : __ldg(rowstat + plane * n_bags + b[k]);
         ++cnt;
-        const float dlt = a - mean;
-        mean += __fdividef(dlt, (float)cnt);
-        m2 = fmaf(dlt, a - mean, m2);
+        const float inv_cnt = __fdividef(1.0f, (float)cnt);
+#pragma unroll
+        for (int k = 0; k < COL_VEC; ++k) {
+          const float a = __expf(lg[k] - rs[k].x) * rs[k].y;
+          if (A && g0 + k < R) A[plane * R + g0 + k] = a;
+          const float dlt = a - mean[k];
+          mean[k] += dlt * inv_cnt;
+          m2[k] = fmaf(dlt, a - mean[k], m2[k]);
+        }
       }
     }
-    s_mean[grp][lane] = mean; s_m2[grp][lane] = m2;
+#pragma unroll
+    for (int k = 0; k < COL_VEC; ++k) { s_mean[grp][lane * COL_VEC + k] = mean[k]; s_m2[grp][lane * COL_VEC + k] = m2[k]; }
     __syncthreads();
-    if (grp == 0 && g < R) {
-      float n_a = (float)cnt;          // group 0 always has the most samples
+    const int col = threadIdx.x, g = blockIdx.x * COL_COLS + col;
+    if (col < COL_COLS && g < R) {
+      float mu = s_mean[0][col], q = s_m2[0][col];
+      float n_a = (float)((T + COL_TGROUPS - 1) / COL_TGROUPS);   // group 0 always has the most samples
 #pragma unroll
       for (int k = 1; k < COL_TGROUPS; ++k) {
         const int nk = (T - k + COL_TGROUPS - 1) / COL_TGROUPS;   // samples of group k
         if (nk <= 0) continue;
-        const float n_b = (float)nk, mb = s_mean[k][lane], qb = s_m2[k][lane];
-        const float n_ab = n_a + n_b, dlt = mb - mean;
-        mean += dlt * __fdividef(n_b, n_ab);
-        m2 += qb + dlt * dlt * __fdividef(n_a * n_b, n_ab);
+        const float n_b = (float)nk, mb = s_mean[k][col], qb = s_m2[k][col];
+        const float n_ab = n_a + n_b, dlt = mb - mu;
+        mu += dlt * __fdividef(n_b, n_ab);
+        q += qb + dlt * dlt * __fdividef(n_a * n_b, n_ab);
         n_a = n_ab;
       }
-      if (attn_mean) attn_mean[(size_t)c * R + g] = mean;
-      if (attn_m2) attn_m2[(size_t)c * R + g] = m2;
+      if (attn_mean) attn_mean[(size_t)c * R + g] = mu;
+      if (attn_m2) attn_m2[(size_t)c * R + g] = q;
     }
   } else {
     if (blockIdx.y != 0 || prob_mean == nullptr) return;
@@ -158,7 +177,7 @@ cudaError_t launch_reduce(const Plan& p, const float* logits, const float* score
     if (e != cudaSuccess) return e;
   }
   if (launches) ++*launches;
-  const int col_blocks = (p.R + COL_LANES - 1) / COL_LANES;
+  const int col_blocks = (p.R + COL_COLS - 1) / COL_COLS;
   const int bag_blocks = (p.n_bags + COL_TGROUPS - 1) / COL_TGROUPS;
   {
     PdlLaunch L(dim3(col_blocks + bag_blocks, p.C), dim3(COL_THREADS), 0, st);
