@@ -60,8 +60,53 @@ softmax_rows_kernel(const float* __restrict__ logits, const float* __restrict__ 
 #pragma unroll
     for (int w = 0; w < ROW_THREADS / 32; ++w) { zz += red[0][w]; yy += red[1][w]; }
     const float inv = 1.0f / zz;
-    rowstat[((size_t)t * C + c) * n_bags + b] = make_float2(m, inv);
+    rowstat[((size_t)c * n_bags + b) * T + t] = make_float2(m, inv);   // [C][n_bags][T]: a row's samples are contiguous
     Y[((size_t)b * T + t) * C + c] = yy * inv;
+  }
+}
+
+// Short rows (every bag <= 32 * VPL patches): one WARP per (bag, t, c) row, eight rows per CTA.  The logits of
+// the row stay in registers between the max and the exp / sum pass (each plane is read from DRAM exactly
+// once), no shared memory, no __syncthreads; the fixed shuffle order keeps the result deterministic.
+template <int VPL>
+__global__ void __launch_bounds__(ROW_THREADS)
+softmax_rows_warp_kernel(const float* __restrict__ logits, const float* __restrict__ scores,
+                         const int32_t* __restrict__ cu, int n_bags, int T, int C, int Rp,
+                         float2* __restrict__ rowstat, float* __restrict__ Y) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");         // logits / scores of the projection kernel
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
+  if (row >= (long long)n_bags * T * C) return;
+  const int c = (int)(row % C);
+  const int t = (int)((row / C) % T);
+  const int b = (int)(row / ((long long)C * T));
+  const int r0 = cu[b], n = cu[b + 1] - r0;
+  const float* lg = logits + ((size_t)t * C + c) * Rp + r0;
+  const float* sc = scores + ((size_t)t * C + c) * Rp + r0;
+  float v[VPL], w[VPL];                                      // both planes of the row in flight at once
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = i < n ? __ldg(lg + i) : -INFINITY;
+    w[k] = i < n ? __ldg(sc + i) : 0.f;
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) m = fmaxf(m, v[k]);
+  m = warp_max(m);
+  float z = 0.f, y = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const float e = __expf(v[k] - m);                        // exp(-inf) = 0 for the padding
+    z += e;
+    y = fmaf(e, w[k], y);
+  }
+  z = warp_sum(z); y = warp_sum(y);
+  if (lane == 0) {
+    const float inv = 1.0f / z;
+    rowstat[((size_t)c * n_bags + b) * T + t] = make_float2(m, inv);   // [C][n_bags][T]: a row's samples are contiguous
+    Y[((size_t)b * T + t) * C + c] = y * inv;
   }
 }
 
@@ -96,16 +141,16 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
 #pragma unroll
       for (int k = 0; k < COL_VEC; ++k) b[k] = row2bag[min(g0 + k, R - 1)];
       const bool one_bag = b[0] == b[COL_VEC - 1];
-#pragma unroll 4
+#pragma unroll 2
       for (int t = grp; t < T; t += COL_TGROUPS) {
         const size_t plane = (size_t)t * C + c;
         // rows >= R of the last float4 are padding of the plane (never written, never used below)
         const float4 l4 = __ldg(reinterpret_cast<const float4*>(logits + plane * Rp + g0));
         const float lg[COL_VEC] = {l4.x, l4.y, l4.z, l4.w};
         float2 rs[COL_VEC];
-        rs[0] = __ldg(rowstat + plane * n_bags + b[0]);
+        rs[0] = __ldg(rowstat + ((size_t)c * n_bags + b[0]) * T + t);
 #pragma unroll
-        for (int k = 1; k < COL_VEC; ++k) rs[k] = one_bag ? rs[0] : __ldg(rowstat + plane * n_bags + b[k]);
+        for (int k = 1; k < COL_VEC; ++k) rs[k] = one_bag ? rs[0] : __ldg(rowstat + ((size_t)c * n_bags + b[k]) * T + t);
         ++cnt;
         const float inv_cnt = __fdividef(1.0f, (float)cnt);
 #pragma unroll
@@ -170,10 +215,17 @@ cudaError_t launch_reduce(const Plan& p, const float* logits, const float* score
                           float* Y, float* A, float* prob_mean, float* prob_m2, float* attn_mean,
                           float* attn_m2, cudaStream_t st, int* launches) {
   {
-    PdlLaunch L(dim3(p.n_bags * p.T * p.C), dim3(ROW_THREADS), 0, st);
     const int32_t* cu = p.d_cu;
     int n_bags = p.n_bags, T = p.T, C = p.C, Rp = p.Rp;
-    cudaError_t e = cudaLaunchKernelEx(&L.cfg, softmax_rows_kernel, logits, scores, cu, n_bags, T, C, Rp, rowstat, Y);
+    const long long rows = (long long)p.n_bags * p.T * p.C;
+    cudaError_t e;
+    if (p.max_n <= 32 * 32 && rows >= 4096) {        // enough short rows to fill the GPU with one warp per row
+      PdlLaunch L(dim3((unsigned)((rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32))), dim3(ROW_THREADS), 0, st);
+      e = cudaLaunchKernelEx(&L.cfg, softmax_rows_warp_kernel<32>, logits, scores, cu, n_bags, T, C, Rp, rowstat, Y);
+    } else {
+      PdlLaunch L(dim3((unsigned)rows), dim3(ROW_THREADS), 0, st);
+      e = cudaLaunchKernelEx(&L.cfg, softmax_rows_kernel, logits, scores, cu, n_bags, T, C, Rp, rowstat, Y);
+    }
     if (e != cudaSuccess) return e;
   }
   if (launches) ++*launches;
