@@ -116,11 +116,16 @@ constexpr int COL_COLS = COL_LANES * COL_VEC;   // packed rows per CTA
 constexpr int COL_TGROUPS = 8;    // MC samples are strided over 8 warps, then merged in a fixed order
 constexpr int COL_THREADS = COL_LANES * COL_TGROUPS;
 
-// grid.x < col_blocks: CTA = 128 packed rows x one head; warp g runs Welford over the samples
-//   t = g, g+8, ... of A[t,c,row], each lane on 4 adjacent rows (one float4 of the logit plane per sample:
-//   512 B per warp and load, 8 independent warps per CTA), then the 8 partial (count, mean, M2) per row are
-//   merged with Chan's formula in warp order 0..7 (deterministic).  Optionally stores A.
+constexpr int COL_CHUNK_T = 64;   // samples staged in shared memory at a time (32 KB)
+
+// grid.x < col_blocks: CTA = 128 packed rows x one head.  The CTA's slab of the logit planes ([T][128] floats,
+//   512 contiguous bytes per sample) is staged through shared memory with cp.async in chunks of 64 samples:
+//   every thread has 8 independent 16-byte copies in flight without holding registers, several CTAs per SM
+//   overlap their copy and compute phases.  Warp g then runs Welford over the samples t = g, g+8, ... of
+//   A[t,c,row], each lane on 4 adjacent rows, and the 8 partial (count, mean, M2) per row are merged with
+//   Chan's formula in warp order 0..7 (deterministic).  Optionally stores A.
 // grid.x >= col_blocks: one warp per bag: mean / M2 over t of softmax_c(Y[bag][t][:])
+template <bool HAS_A>
 __global__ void __launch_bounds__(COL_THREADS)
 welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__ rowstat,
                     const int32_t* __restrict__ row2bag, const float* __restrict__ Y,
@@ -131,37 +136,62 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
   asm volatile("griddepcontrol.wait;" ::: "memory");         // rowstat / Y of softmax_rows_kernel
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if ((int)blockIdx.x < col_blocks) {
+    __shared__ __align__(16) float s_lg[COL_CHUNK_T][COL_COLS];
     __shared__ float s_mean[COL_TGROUPS][COL_COLS], s_m2[COL_TGROUPS][COL_COLS];
     const int c = blockIdx.y;
-    const int g0 = blockIdx.x * COL_COLS + lane * COL_VEC;   // multiple of 4; the planes have stride Rp (multiple of 32)
+    const int col0 = blockIdx.x * COL_COLS;
+    const int g0 = col0 + lane * COL_VEC;                    // multiple of 4; the planes have stride Rp (multiple of 32)
     float mean[COL_VEC] = {0.f, 0.f, 0.f, 0.f}, m2[COL_VEC] = {0.f, 0.f, 0.f, 0.f};
     int cnt = 0;
-    if (g0 < R) {
-      int b[COL_VEC];
+    int b[COL_VEC];
 #pragma unroll
-      for (int k = 0; k < COL_VEC; ++k) b[k] = row2bag[min(g0 + k, R - 1)];
-      const bool one_bag = b[0] == b[COL_VEC - 1];
-#pragma unroll 2
-      for (int t = grp; t < T; t += COL_TGROUPS) {
-        const size_t plane = (size_t)t * C + c;
-        // rows >= R of the last float4 are padding of the plane (never written, never used below)
-        const float4 l4 = __ldg(reinterpret_cast<const float4*>(logits + plane * Rp + g0));
-        const float lg[COL_VEC] = {l4.x, l4.y, l4.z, l4.w};
-        float2 rs[COL_VEC];
-        rs[0] = __ldg(rowstat + ((size_t)c * n_bags + b[0]) * T + t);
-#pragma unroll
-        for (int k = 1; k < COL_VEC; ++k) rs[k] = one_bag ? rs[0] : __ldg(rowstat + ((size_t)c * n_bags + b[k]) * T + t);
-        ++cnt;
-        const float inv_cnt = __fdividef(1.0f, (float)cnt);
-#pragma unroll
-        for (int k = 0; k < COL_VEC; ++k) {
-          const float a = __expf(lg[k] - rs[k].x) * rs[k].y;
-          if (A && g0 + k < R) A[plane * R + g0 + k] = a;
-          const float dlt = a - mean[k];
-          mean[k] += dlt * inv_cnt;
-          m2[k] = fmaf(dlt, a - mean[k], m2[k]);
+    for (int k = 0; k < COL_VEC; ++k) b[k] = row2bag[min(g0 + k, R - 1)];
+    const bool one_bag = b[0] == b[COL_VEC - 1];
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(&s_lg[0][0]);
+    for (int t0 = 0; t0 < T; t0 += COL_CHUNK_T) {
+      const int nt = min(COL_CHUNK_T, T - t0);
+      // 16-byte pieces of the [nt][128] slab; columns >= Rp do not exist (columns in [R, Rp) are plane padding:
+      // copied, never used)
+      for (int p = threadIdx.x; p < nt * (COL_COLS / 4); p += COL_THREADS) {
+        const int row = p / (COL_COLS / 4), seg = p % (COL_COLS / 4);
+        const int gcol = col0 + seg * 4;
+        if (gcol < Rp) {
+          const float* src = logits + ((size_t)(t0 + row) * C + c) * Rp + gcol;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s_base + (uint32_t)(row * COL_COLS + seg * 4) * 4u), "l"(src) : "memory");
         }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      if (g0 < R) {
+        const float2* rs_row = rowstat + ((size_t)c * n_bags + b[0]) * T + t0;
+#pragma unroll 4
+        for (int r = grp; r < nt; r += COL_TGROUPS) {
+          const float4 l4 = *reinterpret_cast<const float4*>(&s_lg[r][lane * COL_VEC]);
+          const float lg[COL_VEC] = {l4.x, l4.y, l4.z, l4.w};
+          float2 rs[COL_VEC];
+          rs[0] = __ldg(rs_row + r);
+#pragma unroll
+          for (int k = 1; k < COL_VEC; ++k) rs[k] = rs[0];
+          if (!one_bag) {                                    // a bag boundary inside this lane's four rows (rare)
+#pragma unroll
+            for (int k = 1; k < COL_VEC; ++k) rs[k] = __ldg(rowstat + ((size_t)c * n_bags + b[k]) * T + t0 + r);
+          }
+          ++cnt;
+          const float inv_cnt = __fdividef(1.0f, (float)cnt);
+#pragma unroll
+          for (int k = 0; k < COL_VEC; ++k) {
+            const float a = __expf(lg[k] - rs[k].x) * rs[k].y;
+            if constexpr (HAS_A) {
+              if (g0 + k < R) A[((size_t)(t0 + r) * C + c) * R + g0 + k] = a;
+            }
+            const float dlt = a - mean[k];
+            mean[k] += dlt * inv_cnt;
+            m2[k] = fmaf(dlt, a - mean[k], m2[k]);
+          }
+        }
+      }
+      __syncthreads();                                       // the next chunk overwrites s_lg
     }
 #pragma unroll
     for (int k = 0; k < COL_VEC; ++k) { s_mean[grp][lane * COL_VEC + k] = mean[k]; s_m2[grp][lane * COL_VEC + k] = m2[k]; }
@@ -237,8 +267,11 @@ cudaError_t launch_reduce(const Plan& p, const float* logits, const float* score
     const int32_t* r2b = p.d_row2bag;
     const float* Yc = Y;
     int n_bags = p.n_bags, T = p.T, C = p.C, R = p.R, Rp = p.Rp;
-    cudaError_t e = cudaLaunchKernelEx(&L.cfg, welford_cols_kernel, logits, rs, r2b, Yc, n_bags, T, C, R, Rp, col_blocks,
-                                       A, attn_mean, attn_m2, prob_mean, prob_m2);
+    cudaError_t e = A != nullptr
+        ? cudaLaunchKernelEx(&L.cfg, welford_cols_kernel<true>, logits, rs, r2b, Yc, n_bags, T, C, R, Rp, col_blocks,
+                             A, attn_mean, attn_m2, prob_mean, prob_m2)
+        : cudaLaunchKernelEx(&L.cfg, welford_cols_kernel<false>, logits, rs, r2b, Yc, n_bags, T, C, R, Rp, col_blocks,
+                             A, attn_mean, attn_m2, prob_mean, prob_m2);
     if (e != cudaSuccess) return e;
   }
   if (launches) ++*launches;
