@@ -4,6 +4,7 @@
 #include <cmath>
 #include <new>
 #include <string>
+#include <cstdlib>
 #include "internal.h"
 
 using namespace mcmil;
@@ -136,8 +137,6 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu, const int32_t* bag_
   p->off_logit = off;   off = align_up(off + (size_t)T * p->C * p->Rp * sizeof(float), 1024);
   p->off_score = off;   off = align_up(off + (size_t)T * p->C * p->Rp * sizeof(float), 1024);
   p->off_rowstat = off; off = align_up(off + (size_t)T * p->C * n_bags * sizeof(float2), 1024);
-  p->maskcache_bytes = p->C > 1 ? (size_t)T * p->R * 64 : 0;
-  p->off_maskcache = off; off = align_up(off + p->maskcache_bytes, 1024);
   p->ws_bytes = off;
   *out = p;
   return 0;
@@ -182,8 +181,7 @@ int mcmil_head_forward(const mcmil_weights_t* w, const mcmil_plan_t* plan, const
   if (impl == MCMIL_IMPL_TCGEN05) {
     const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
     if (prof) cudaEventRecord(g_prof.ev[g_prof.used], st);
-    uint8_t* mask_cache = (w->S > 1 && plan->maskcache_bytes > 0) ? ws + plan->off_maskcache : nullptr;
-    e = launch_proj_tc(*w, *plan, m, H, logits, scores, mask_cache, nullptr, st, &g_launches);
+    e = launch_proj_tc(*w, *plan, m, H, logits, scores, nullptr, st, &g_launches);
     if (prof) { cudaEventRecord(g_prof.ev[g_prof.used + 1], st); g_prof.used += 2; g_prof.kernels += w->S; }
     if (e != cudaSuccess) return cuda_fail(e, "proj_tc");
   } else if (impl == MCMIL_IMPL_SIMT_FP32) {
@@ -211,7 +209,7 @@ int mcmil_debug_proj_tc(const mcmil_weights_t* w, const mcmil_plan_t* plan, cons
   float* scores = reinterpret_cast<float*>(ws + plan->off_score);
   const MaskSpec m = make_mask_spec(t_offset, bag_offset, seed, 10, p_f, p_a, inj_feat, inj_attn);
   int launches = 0;
-  cudaError_t e = launch_proj_tc(*w, *plan, m, H, logits, scores, nullptr, dbg, st, &launches);
+  cudaError_t e = launch_proj_tc(*w, *plan, m, H, logits, scores, dbg, st, &launches);
   const size_t plane = (size_t)plan->T * plan->C * plan->Rp * sizeof(float);
   if (e == cudaSuccess && logits_out) e = cudaMemcpyAsync(logits_out, logits, plane, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess && scores_out) e = cudaMemcpyAsync(scores_out, scores, plane, cudaMemcpyDeviceToDevice, st);

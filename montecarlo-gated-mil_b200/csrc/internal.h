@@ -36,8 +36,7 @@ struct Plan {
   int32_t* d_row2bag = nullptr;  // [R]
   int32_t* d_gbag = nullptr;     // [n_bags] global bag ids
   // workspace layout (byte offsets)
-  size_t off_logit = 0, off_score = 0, off_rowstat = 0, off_maskcache = 0, ws_bytes = 0;
-  size_t maskcache_bytes = 0;   // T*R*64 keep bytes, reserved when num_classes > 1 (used by separate attention)
+  size_t off_logit = 0, off_score = 0, off_rowstat = 0, ws_bytes = 0;
 };
 
 struct MaskSpec {
@@ -70,8 +69,7 @@ cudaError_t launch_pack_weights(Weights& w, const float* attV_w, const float* at
                                 const float* attU_b, const float* attw_w, const float* attw_b,
                                 const float* cls_w, cudaStream_t st);
 cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const float* H,
-                           float* logits, float* scores, uint8_t* mask_cache, float* dbg, cudaStream_t st,
-                           int* launches);
+                           float* logits, float* scores, float* dbg, cudaStream_t st, int* launches);
 cudaError_t launch_proj_simt(const Weights& w, const Plan& p, const MaskSpec& m, const float* H,
                              float* logits, float* scores, cudaStream_t st, int* launches);
 cudaError_t launch_reduce(const Plan& p, const float* logits, const float* scores, float2* rowstat,

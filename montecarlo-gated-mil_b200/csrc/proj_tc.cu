@@ -64,10 +64,7 @@ static_assert(SM_TOTAL <= 232448, "227 KB of dynamic shared memory per CTA");
 // where the feature keep-masks come from
 enum : int {
   MASK_PHILOX = 0,         // drawn in the kernel
-  MASK_INJECTED = 1,       // caller-provided bits (parity tests with the reference's own masks)
-  MASK_PHILOX_EXPORT = 2,  // drawn in the kernel and written to the mask cache (separate attention, first head)
-  MASK_CACHED = 3          // read back from the mask cache (separate attention, remaining heads): the SAME
-                           // H_drop feeds every head (model.py:281,297-298) without paying the RNG again
+  MASK_INJECTED = 1        // caller-provided bits (parity tests with the reference's own masks)
 };
 
 // barrier slots (8 bytes each) inside SM_BAR.  The ring barriers and the accumulator-empty barrier
@@ -101,7 +98,6 @@ struct ProjParams {
   float* scores;           // [T][C][Rp]
   const uint32_t* inj_feat;  // [T][R][16] or null
   const uint32_t* inj_attn;  // [T][C][Rp/32] or null
-  uint8_t* mask_cache;     // [T][R][8 chunks-in-slice][TEAMS][TEAM_SLICES] keep bytes, or null
   float* dbg;              // optional raw accumulator dump of each pair's first (tile, t)
   int n_tiles, T, C, R, Rp;
   int n_out;               // heads produced by this launch (shared: C, separate: 1)
@@ -157,36 +153,6 @@ __device__ __forceinline__ uint32_t keep_mask2_alu(uint32_t r, uint32_t thr2) {
   const uint32_t b = (r | 0x80008000u) - thr2;
   uint32_t m;
   asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(m) : "r"(b));
-  return m;
-}
-// keep byte (bit e <-> feature 8q+e) from the four all-ones/zero lane-pair masks; only byte 0 of the
-// result is meaningful
-__device__ __forceinline__ uint32_t keep_byte(const uint4& m) {
-  const uint32_t b = (m.x & 0x00020001u) | (m.y & 0x00080004u) | (m.z & 0x00200010u) | (m.w & 0x00800040u);
-  return b | (b >> 16);
-}
-// byte SI of w replaced by byte 0 of b
-template <int SI>
-__device__ __forceinline__ uint32_t insert_byte(uint32_t w, uint32_t b) {
-  constexpr uint32_t sel = SI == 0 ? 0x3214u : SI == 1 ? 0x3240u : SI == 2 ? 0x3410u : 0x4210u;
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(b), "n"(sel));
-  return r;
-}
-// Inverse of keep_byte without a table: byte SI of w -> the four lane-pair masks.  Two multiplies move
-// keep bit e to the top bit of byte e (of two words), PRMT's sign-replicate mode widens each top bit
-// to a 16-bit lane.  13 ALU-type instructions per chunk instead of a Philox call.
-template <int SI>
-__device__ __forceinline__ uint4 expand_keep_byte(uint32_t w) {
-  uint32_t kb;
-  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(kb) : "r"(w), "n"(0x4440 | SI));
-  const uint32_t lo = (kb & 0x0Fu) * 0x10204080u;      // bit e -> bit 8e+7, e = 0..3
-  const uint32_t hi = (kb & 0xF0u) * 0x01020408u;      // bit e -> bit 8(e-4)+7, e = 4..7
-  uint4 m;
-  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(m.x) : "r"(lo));
-  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(m.y) : "r"(lo));
-  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(m.z) : "r"(hi));
-  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(m.w) : "r"(hi));
   return m;
 }
 // The four lane-pair keep masks of one (row, chunk) from its 8 primary bytes (wa: features 0..3,
@@ -266,7 +232,7 @@ template <int NOUT, int MASK, bool DEBUG, int ROUNDS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 proj_tc_kernel(const __grid_constant__ ProjParams P) {
   constexpr bool INJECT = MASK == MASK_INJECTED;            // logit masks injected too
-  constexpr bool DRAW = MASK == MASK_PHILOX || MASK == MASK_PHILOX_EXPORT;
+  constexpr bool DRAW = MASK == MASK_PHILOX;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -483,37 +449,11 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         rnd[0] = philox4x32<ROUNDS>(q0, nrow[0], tg0, bag, P.key);
         rnd[1] = philox4x32<ROUNDS>(q0, nrow[2], tg0, bag, P.key);
       }
-      // mask cache (separate attention): one 64-byte record per (sample, packed row), byte
-      // [chunk][team][si] = keep bits of chunk (TEAMS*si+team)*8+chunk; a thread owns one 32-bit word
-      // of it per row slot and sample.
-      static_assert(!(MASK == MASK_PHILOX_EXPORT || MASK == MASK_CACHED) || (TEAMS == 2 && TEAM_SLICES == 4),
-                    "mask cache layout assumes two producer teams");
-      size_t crow[4];
-      bool rvalid[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        rvalid[i] = (int)rank * HALF_ROWS + rowi[i] < td.nrows;
-        crow[i] = (size_t)(td.row0 + (int)rank * HALF_ROWS + rowi[i]) * 64 + chunk * 8 + team * 4;
-      }
-      uint32_t cw[4] = {0u, 0u, 0u, 0u};
-      if constexpr (MASK == MASK_CACHED) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (rvalid[i]) cw[i] = __ldg(reinterpret_cast<const uint32_t*>(P.mask_cache + (size_t)t_begin * P.R * 64 + crow[i]));
-      }
 #pragma unroll 1
       for (int t = t_begin; t < t_end; ++t, ++tc) {
         const uint32_t tg = (uint32_t)(P.t_offset + t);
         // slot s was last read by the MMAs of sample tc-1, issued by warp (tc-1)&1 as its ((tc-1)>>1)-th
         const uint32_t full_set = (tc & (NMMA - 1)) * NSLICE;
-        uint32_t cnext[4] = {0u, 0u, 0u, 0u};
-        if constexpr (MASK == MASK_CACHED) {                   // prefetch the next sample's keep bytes
-          if (t + 1 < t_end) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (rvalid[i]) cnext[i] = __ldg(reinterpret_cast<const uint32_t*>(P.mask_cache + (size_t)(t + 1) * P.R * 64 + crow[i]));
-          }
-        }
 #pragma unroll
         for (int si = 0; si < TEAM_SLICES; ++si) {
           const int s = TEAMS * si + team;
@@ -551,12 +491,6 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 #else
               m = keep_masks(wa, wb, rw, si, thr2);
 #endif
-              if constexpr (MASK == MASK_PHILOX_EXPORT)
-                cw[i] = si == 0 ? insert_byte<0>(cw[i], keep_byte(m)) : si == 1 ? insert_byte<1>(cw[i], keep_byte(m))
-                      : si == 2 ? insert_byte<2>(cw[i], keep_byte(m)) : insert_byte<3>(cw[i], keep_byte(m));
-            } else if constexpr (MASK == MASK_CACHED) {
-              m = si == 0 ? expand_keep_byte<0>(cw[i]) : si == 1 ? expand_keep_byte<1>(cw[i])
-                : si == 2 ? expand_keep_byte<2>(cw[i]) : expand_keep_byte<3>(cw[i]);
             } else {
               const int trow = (int)rank * HALF_ROWS + rowi[i];
               uint32_t bits = 0;
@@ -595,15 +529,6 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
           if (lane0) mbar_arrive_cluster(full_team + (full_set + TEAMS * si) * 8);
           TRACE(tc, 4 * si + 3);
           if constexpr (DRAW) { rnd[0] = nxt[0]; rnd[1] = nxt[1]; ref = ref_nxt; }
-        }
-        if constexpr (MASK == MASK_PHILOX_EXPORT) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (rvalid[i]) *reinterpret_cast<uint32_t*>(P.mask_cache + (size_t)t * P.R * 64 + crow[i]) = cw[i];
-        }
-        if constexpr (MASK == MASK_CACHED) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) cw[i] = cnext[i];
         }
       }
       u = u_next < u_end ? u_next : u_end;
@@ -724,30 +649,24 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 }
 
 cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const float* H,
-                           float* logits, float* scores, uint8_t* mask_cache, float* dbg, cudaStream_t st,
-                           int* launches) {
+                           float* logits, float* scores, float* dbg, cudaStream_t st, int* launches) {
   using KernelFn = void (*)(ProjParams);
-  // [rounds 10 / 7][mask source][heads per launch]; export / cached exist for one head per launch only
-  static const KernelFn kernels[2][4][4] = {
+  // [rounds 10 / 7][mask source][heads per launch]
+  static const KernelFn kernels[2][2][4] = {
       {{proj_tc_kernel<1, MASK_PHILOX, false, 10>, proj_tc_kernel<2, MASK_PHILOX, false, 10>,
         proj_tc_kernel<3, MASK_PHILOX, false, 10>, proj_tc_kernel<4, MASK_PHILOX, false, 10>},
        {proj_tc_kernel<1, MASK_INJECTED, false, 10>, proj_tc_kernel<2, MASK_INJECTED, false, 10>,
-        proj_tc_kernel<3, MASK_INJECTED, false, 10>, proj_tc_kernel<4, MASK_INJECTED, false, 10>},
-       {proj_tc_kernel<1, MASK_PHILOX_EXPORT, false, 10>, nullptr, nullptr, nullptr},
-       {proj_tc_kernel<1, MASK_CACHED, false, 10>, nullptr, nullptr, nullptr}},
+        proj_tc_kernel<3, MASK_INJECTED, false, 10>, proj_tc_kernel<4, MASK_INJECTED, false, 10>}},
       {{proj_tc_kernel<1, MASK_PHILOX, false, 7>, proj_tc_kernel<2, MASK_PHILOX, false, 7>,
         proj_tc_kernel<3, MASK_PHILOX, false, 7>, proj_tc_kernel<4, MASK_PHILOX, false, 7>},
        {proj_tc_kernel<1, MASK_INJECTED, false, 10>, proj_tc_kernel<2, MASK_INJECTED, false, 10>,
-        proj_tc_kernel<3, MASK_INJECTED, false, 10>, proj_tc_kernel<4, MASK_INJECTED, false, 10>},
-       {proj_tc_kernel<1, MASK_PHILOX_EXPORT, false, 7>, nullptr, nullptr, nullptr},
-       {proj_tc_kernel<1, MASK_CACHED, false, 7>, nullptr, nullptr, nullptr}}};
+        proj_tc_kernel<3, MASK_INJECTED, false, 10>, proj_tc_kernel<4, MASK_INJECTED, false, 10>}}};
   static const KernelFn debug_kernel = proj_tc_kernel<2, MASK_PHILOX, true, 10>;   // raw-accumulator dump (tests only)
   static bool attr_set = false;
   if (!attr_set) {
     for (int r = 0; r < 2; ++r)
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 4; ++b) {
-          if (kernels[r][a][b] == nullptr) continue;
           cudaError_t e = cudaFuncSetAttribute(kernels[r][a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
           if (e != cudaSuccess) return e;
         }
@@ -775,7 +694,6 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
     P.tiles = p.d_tiles;
     P.logits = logits; P.scores = scores;
     P.inj_feat = m.inj_feat; P.inj_attn = m.inj_attn;
-    P.mask_cache = mask_cache;
     P.dbg = dbg;
     P.n_tiles = p.n_tiles; P.T = p.T; P.C = p.C; P.R = p.R; P.Rp = p.Rp;
     P.n_out = w.shared ? w.C : 1;
@@ -785,9 +703,9 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
     P.sf = m.sf; P.hsf = 0.5f * m.sf; P.sa = m.sa;
     P.key = m.key;
     P.epi = w.epi[s];
-    // separate attention: the first head draws the masks and exports them, the others read them back
-    int mask_mode = m.inj_feat != nullptr ? MASK_INJECTED : MASK_PHILOX;
-    if (mask_mode == MASK_PHILOX && w.S > 1 && mask_cache != nullptr) mask_mode = s == 0 ? MASK_PHILOX_EXPORT : MASK_CACHED;
+    // separate attention: every head's launch redraws the same Philox masks (the same H_drop feeds all heads,
+    // model.py:281,297-298); a keep-bit cache in HBM was measured no faster once a call costs 1/16 per element
+    const int mask_mode = m.inj_feat != nullptr ? MASK_INJECTED : MASK_PHILOX;
     const KernelFn fn = dbg != nullptr ? debug_kernel : kernels[m.rounds == 7 ? 1 : 0][mask_mode][P.n_out - 1];
     {
       PdlLaunch L(dim3(2 * n_pairs), dim3(TC_THREADS), SM_TOTAL, st);
