@@ -129,6 +129,9 @@ __device__ __forceinline__ uint32_t bar_addr(uint32_t sbase, uint32_t slot) { re
 #ifndef MCMIL_RELAXED_NS_TFULL
 #define MCMIL_RELAXED_NS_TFULL 128      // epilogue warps waiting for the next accumulator (multi-buffered)
 #endif
+#ifndef MCMIL_RELAXED_NS_FULL
+#define MCMIL_RELAXED_NS_FULL 0         // issue warps waiting for the next K-slice: plain try_wait (32 / 64 / 128 ns polling: no difference)
+#endif
 #ifdef MCMIL_EXP_WAITSTATS
 #define WAIT_T(acc, bar, parity) do { const long long w0_ = clock64(); mbar_wait(bar, parity); acc += clock64() - w0_; } while (0)
 #define WAIT_R(acc, bar, parity, ns) do { const long long w0_ = clock64(); if ((ns) > 0) mbar_wait_relaxed(bar, parity, ns); else mbar_wait(bar, parity); acc += clock64() - w0_; } while (0)
@@ -325,7 +328,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         bool full_ready = false;                                // early probe of the next slice's FULL barrier
 #pragma unroll 1
         for (int s = 0; s < NSLICE; ++s) {
-          if (!full_ready) WAIT_T(wait_a, bar_addr(sbase, B_FULL + q * NSLICE + s), j & 1);
+          if (!full_ready) WAIT_R(wait_a, bar_addr(sbase, B_FULL + q * NSLICE + s), j & 1, MCMIL_RELAXED_NS_FULL);
           tc_fence_after();
 #ifndef MCMIL_NO_EARLY_PROBE
           full_ready = s + 1 < NSLICE && mbar_test_wait(bar_addr(sbase, B_FULL + q * NSLICE + s + 1), j & 1);
