@@ -1,7 +1,7 @@
 """Smallest end-to-end invocation of the hot path, for compute-sanitizer (one tool per gpurun call)."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import mcmil_b200 as mm
 from oracle import gamil_oracle as G
 dev = torch.device("cuda")
