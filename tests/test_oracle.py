@@ -48,6 +48,35 @@ def test_threshold_and_rates():
     assert np.array_equal(PX.attn_keep(5, 0, 2, 4, 40, 3, 0.1), ka[2:])
 
 
+def test_feature_mask_stream_statistics():
+    """The 16-elements-per-call mask stream behaves like iid Bernoulli(1 - p): drop rate at 4 sigma, and no
+    correlation between the pairs that share Philox words (features of a chunk share the refinement byte, rows n
+    and n^4 share the primary call, rows n..n+12 share the refinement call), neighbouring samples or K-slices."""
+    T, N, p = 8, 512, 0.1
+    k = PX.feature_keep(2024, 3, 0, T, N, p).astype(np.float64)            # 2.1 M elements
+    q = 3277 / 32768
+    n = k.size
+    assert abs((1 - k.mean()) - q) < 4 * np.sqrt(q * (1 - q) / n)
+    d = 1.0 - k - q                                                        # centred drop indicators
+
+    def corr(a, b):
+        return float((a * b).mean() / (q * (1 - q)))
+
+    tol = 5 / np.sqrt(n / 2)                                               # ~5 sigma for 1 M pairs
+    assert abs(corr(d[:, :, 0::2], d[:, :, 1::2])) < tol                   # neighbouring features (same chunk)
+    assert abs(corr(d[:, :, :-8], d[:, :, 8:])) < tol                      # same lane of neighbouring chunks
+    assert abs(corr(d[:, :, :-64], d[:, :, 64:])) < tol                    # neighbouring K-slices
+    idx = np.arange(N)
+    lo = idx[(idx & 4) == 0]
+    assert abs(corr(d[:, lo, :], d[:, lo + 4, :])) < tol                   # rows n, n^4 (same primary call)
+    lo8 = idx[(idx & 8) == 0]
+    assert abs(corr(d[:, lo8, :], d[:, lo8 + 8, :])) < tol                 # rows n, n+8 (same refinement call)
+    assert abs(corr(d[:-1], d[1:])) < tol                                  # consecutive MC samples
+    # every feature position has the same rate (no byte of the call is biased)
+    per_l = 1 - k.mean(axis=(0, 1))
+    assert np.abs(per_l - q).max() < 6 * np.sqrt(q * (1 - q) / (T * N))
+
+
 def test_pack_bits_roundtrip():
     rng = np.random.default_rng(0)
     k = (rng.random((3, 5, 77)) < 0.9).astype(np.uint8)
