@@ -297,15 +297,16 @@ def run_ours(args):
                    "kernel_ms": k7, "roofline_frac": (flops_step / S) / (k7 * 1e-3) / 1e12 / peak if k7 > 0 else None}
 
     # ---- e2e: pinned-host features in, results out, through the public API, inside the timed region
-    e2e = None
-    if not args.no_e2e:
+    e2e, e2e_f16 = None, None
+
+    def measure_e2e(dtype):
         chunk_bags = max(1, min(n_bags, args.e2e_chunk))
-        H_host = torch.empty((R, L), dtype=torch.float32).pin_memory()
-        H_host.copy_(H.cpu())
+        H_host = torch.empty((R, L), dtype=dtype).pin_memory()
+        H_host.copy_(H.to(dtype).cpu())
         streams = [torch.cuda.Stream(dev) for _ in range(2)]
         n_chunks = (n_bags + chunk_bags - 1) // chunk_bags
         max_rows = max(int(cu[min(n_bags, (k + 1) * chunk_bags)] - cu[k * chunk_bags]) for k in range(n_chunks))
-        dbuf = [torch.empty((max_rows, L), dtype=torch.float32, device=dev) for _ in range(2)]
+        dbuf = [torch.empty((max_rows, L), dtype=dtype, device=dev) for _ in range(2)]
         # results land in flat pinned buffers (one per chunk): every D2H copy is a single contiguous
         # cudaMemcpyAsync (a strided pinned destination makes torch stage + synchronise, which
         # serialises the whole pipeline)
@@ -318,7 +319,7 @@ def run_ours(args):
             outY[k] = torch.empty((b1 - b0) * T * C, dtype=torch.float32).pin_memory()
             outP[k] = torch.empty(2 * (b1 - b0) * C, dtype=torch.float32).pin_memory()
             outA[k] = torch.empty(2 * C * rows, dtype=torch.float32).pin_memory()
-        h2d = R * L * 4
+        h2d = R * L * H_host.element_size()
         d2h = sum(t.numel() for t in outY + outP + outA) * 4
 
         def e2e_step(i):
@@ -353,9 +354,15 @@ def run_ours(args):
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": job_bags * args.steps / dt, "unit": "bags/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "chunk_bags": chunk_bags, "streams": 2,
-               "api": "mcmil_b200.mc_head on pinned-host features (copy in, compute, copy out, pipelined over 2 streams)"}
+        return {"value": job_bags * args.steps / dt, "unit": "bags/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "chunk_bags": chunk_bags, "streams": 2,
+                "api": "mcmil_b200.mc_head on pinned-host %s features (copy in, compute, copy out, pipelined over 2 streams)"
+                       % ("float32" if dtype == torch.float32 else "float16")}
+
+    if not args.no_e2e:
+        e2e = measure_e2e(torch.float32)                 # the reference's feature dtype: the e2e number of record
+        if not args.no_extras:
+            e2e_f16 = measure_e2e(torch.float16)         # features handed over in half precision (same results)
 
     # ---- single-bag call latency / back-to-back throughput (the reference's bs=1 usage)
     single = None
@@ -411,7 +418,7 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2 (%.0f MB of features per step per GPU), no flush" % (R * L * 4 / 1e6),
                        "parallelism": "bags sharded over ranks, no collective" if args.workload != "config4"
                        else "MC samples sharded over ranks, one NCCL allreduce of Welford partials"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "single_bag": single,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_f16_features": e2e_f16, "single_bag": single,
             "philox_rounds": args.philox_rounds, "philox7_mode": philox7,
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "clocks": clocks, "flops_per_step_per_gpu": flops_step,

@@ -104,6 +104,16 @@ int mcmil_head_forward(const mcmil_weights_t* w, const mcmil_plan_t* plan, const
                        float* attn_mean, float* attn_m2, void* workspace, size_t workspace_bytes,
                        void* stream);
 
+/* Same call for features that already are IEEE half precision (e.g. an extractor run under autocast): H16 is DEVICE
+ * fp16 [R][512].  The tensor-core path rounds fp32 features to fp16 anyway, so for H16 = fp16(H) both entry points
+ * return bit-identical results; this one moves half the bytes (host-to-device copies included). */
+int mcmil_head_forward_f16(const mcmil_weights_t* w, const mcmil_plan_t* plan, const uint16_t* H16,
+                           int t_offset, int bag_offset, uint64_t seed, int philox_rounds, float p_f, float p_a,
+                           const uint32_t* inj_feat_keep_bits, const uint32_t* inj_attn_keep_bits,
+                           int impl, float* Y, float* A, float* prob_mean, float* prob_m2,
+                           float* attn_mean, float* attn_m2, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
 /* ---- Welford merge across MC-sample shards ----------------------------
  * pack:   out[0] = count, out[1+i] = count*mean[i], out[1+n+i] = m2[i] + count*mean[i]^2
  *         (DEVICE fp64 [1+2n]; additive, so ONE allreduce(sum) merges all shards)

@@ -32,6 +32,8 @@ SIGNATURES = {
     "mcmil_plan_total_rows": (_i, [_vp]),
     "mcmil_head_forward": (_i, [_vp, _vp, _vp, _i, _i, _u64, _i, _f, _f, _vp, _vp, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mcmil_head_forward_f16": (_i, [_vp, _vp, _vp, _i, _i, _u64, _i, _f, _f, _vp, _vp, _i,
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mcmil_welford_pack": (_i, [_vp, _vp, _dbl, _i, _vp, _vp]),
     "mcmil_welford_unpack": (_i, [_vp, _i, _vp, _vp, _vp]),
     "mcmil_export_masks": (_i, [_vp, _i, _i, _u64, _i, _f, _f, _vp, _vp, _vp]),

@@ -151,11 +151,11 @@ int mcmil_plan_destroy(mcmil_plan_t* p) {
 size_t mcmil_plan_workspace_bytes(const mcmil_plan_t* p) { return p ? p->ws_bytes : 0; }
 int mcmil_plan_total_rows(const mcmil_plan_t* p) { return p ? p->R : 0; }
 
-int mcmil_head_forward(const mcmil_weights_t* w, const mcmil_plan_t* plan, const float* H,
-                       int t_offset, int bag_offset, uint64_t seed, int philox_rounds, float p_f, float p_a,
-                       const uint32_t* inj_feat, const uint32_t* inj_attn, int impl,
-                       float* Y, float* A, float* prob_mean, float* prob_m2, float* attn_mean, float* attn_m2,
-                       void* workspace, size_t workspace_bytes, void* stream) {
+static int head_forward_impl(const mcmil_weights_t* w, const mcmil_plan_t* plan, const void* H, int h_f16,
+                             int t_offset, int bag_offset, uint64_t seed, int philox_rounds, float p_f, float p_a,
+                             const uint32_t* inj_feat, const uint32_t* inj_attn, int impl,
+                             float* Y, float* A, float* prob_mean, float* prob_m2, float* attn_mean, float* attn_m2,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   g_launches = 0;
   if (!w || !plan || !H || !Y || !workspace) return fail(MCMIL_E_BADARG, "mcmil_head_forward: null pointer");
   if (w->C != plan->C) return fail(MCMIL_E_BADARG, "mcmil_head_forward: weights and plan disagree on num_classes");
@@ -181,11 +181,11 @@ int mcmil_head_forward(const mcmil_weights_t* w, const mcmil_plan_t* plan, const
   if (impl == MCMIL_IMPL_TCGEN05) {
     const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
     if (prof) cudaEventRecord(g_prof.ev[g_prof.used], st);
-    e = launch_proj_tc(*w, *plan, m, H, logits, scores, nullptr, st, &g_launches);
+    e = launch_proj_tc(*w, *plan, m, H, h_f16, logits, scores, nullptr, st, &g_launches);
     if (prof) { cudaEventRecord(g_prof.ev[g_prof.used + 1], st); g_prof.used += 2; g_prof.kernels += w->S; }
     if (e != cudaSuccess) return cuda_fail(e, "proj_tc");
   } else if (impl == MCMIL_IMPL_SIMT_FP32) {
-    e = launch_proj_simt(*w, *plan, m, H, logits, scores, st, &g_launches);
+    e = launch_proj_simt(*w, *plan, m, H, h_f16, logits, scores, st, &g_launches);
     if (e != cudaSuccess) return cuda_fail(e, "proj_simt");
   } else {
     return fail(MCMIL_E_BADARG, "mcmil_head_forward: unknown impl");
@@ -193,6 +193,23 @@ int mcmil_head_forward(const mcmil_weights_t* w, const mcmil_plan_t* plan, const
   e = launch_reduce(*plan, logits, scores, rowstat, Y, A, prob_mean, prob_m2, attn_mean, attn_m2, st, &g_launches);
   if (e != cudaSuccess) return cuda_fail(e, "reduce");
   return 0;
+}
+
+int mcmil_head_forward(const mcmil_weights_t* w, const mcmil_plan_t* plan, const float* H,
+                       int t_offset, int bag_offset, uint64_t seed, int philox_rounds, float p_f, float p_a,
+                       const uint32_t* inj_feat, const uint32_t* inj_attn, int impl,
+                       float* Y, float* A, float* prob_mean, float* prob_m2, float* attn_mean, float* attn_m2,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  return head_forward_impl(w, plan, H, 0, t_offset, bag_offset, seed, philox_rounds, p_f, p_a, inj_feat, inj_attn, impl,
+                           Y, A, prob_mean, prob_m2, attn_mean, attn_m2, workspace, workspace_bytes, stream);
+}
+int mcmil_head_forward_f16(const mcmil_weights_t* w, const mcmil_plan_t* plan, const uint16_t* H16,
+                           int t_offset, int bag_offset, uint64_t seed, int philox_rounds, float p_f, float p_a,
+                           const uint32_t* inj_feat, const uint32_t* inj_attn, int impl,
+                           float* Y, float* A, float* prob_mean, float* prob_m2, float* attn_mean, float* attn_m2,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  return head_forward_impl(w, plan, H16, 1, t_offset, bag_offset, seed, philox_rounds, p_f, p_a, inj_feat, inj_attn, impl,
+                           Y, A, prob_mean, prob_m2, attn_mean, attn_m2, workspace, workspace_bytes, stream);
 }
 
 // Debug entry (not part of the reference-facing surface): runs pack + tcgen05 projection only and
@@ -209,7 +226,7 @@ int mcmil_debug_proj_tc(const mcmil_weights_t* w, const mcmil_plan_t* plan, cons
   float* scores = reinterpret_cast<float*>(ws + plan->off_score);
   const MaskSpec m = make_mask_spec(t_offset, bag_offset, seed, 10, p_f, p_a, inj_feat, inj_attn);
   int launches = 0;
-  cudaError_t e = launch_proj_tc(*w, *plan, m, H, logits, scores, dbg, st, &launches);
+  cudaError_t e = launch_proj_tc(*w, *plan, m, H, 0, logits, scores, dbg, st, &launches);
   const size_t plane = (size_t)plan->T * plan->C * plan->Rp * sizeof(float);
   if (e == cudaSuccess && logits_out) e = cudaMemcpyAsync(logits_out, logits, plane, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess && scores_out) e = cudaMemcpyAsync(scores_out, scores, plane, cudaMemcpyDeviceToDevice, st);

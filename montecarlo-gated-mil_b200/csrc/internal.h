@@ -68,9 +68,9 @@ struct PdlLaunch {
 cudaError_t launch_pack_weights(Weights& w, const float* attV_w, const float* attV_b, const float* attU_w,
                                 const float* attU_b, const float* attw_w, const float* attw_b,
                                 const float* cls_w, cudaStream_t st);
-cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const float* H,
+cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const void* H, int h_f16,
                            float* logits, float* scores, float* dbg, cudaStream_t st, int* launches);
-cudaError_t launch_proj_simt(const Weights& w, const Plan& p, const MaskSpec& m, const float* H,
+cudaError_t launch_proj_simt(const Weights& w, const Plan& p, const MaskSpec& m, const void* H, int h_f16,
                              float* logits, float* scores, cudaStream_t st, int* launches);
 cudaError_t launch_reduce(const Plan& p, const float* logits, const float* scores, float2* rowstat,
                           float* Y, float* A, float* prob_mean, float* prob_m2, float* attn_mean,

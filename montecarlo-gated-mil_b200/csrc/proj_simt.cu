@@ -14,7 +14,8 @@ namespace mcmil {
 constexpr int SM_ROWS = 64, SM_KSTEP = 32, SM_THREADS = 256, A_LD = SM_ROWS + 1;
 
 struct SimtParams {
-  const float* H;       // [R][512]
+  const void* H;        // [R][512] fp32 or (h_f16) fp16
+  int h_f16;
   const float* WT;      // this set: [512][256]
   const float* bv; const float* bu;   // this set: [128]
   const float* ww;      // [C][128]
@@ -59,9 +60,17 @@ proj_simt_kernel(const SimtParams P) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = 0.f;
       if (trow_l < td.nrows) {
-        const float4* src = reinterpret_cast<const float4*>(P.H + (size_t)(td.row0 + trow_l) * L + k0 + lchunk * 8);
-        const float4 a = __ldg(src), b = __ldg(src + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        const size_t e0 = (size_t)(td.row0 + trow_l) * L + k0 + lchunk * 8;
+        if (P.h_f16) {
+          const uint4 hv = __ldg(reinterpret_cast<const uint4*>(static_cast<const __half*>(P.H) + e0));
+          const __half2* h2 = reinterpret_cast<const __half2*>(&hv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h2[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+        } else {
+          const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(P.H) + e0);
+          const float4 a = __ldg(src), b = __ldg(src + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
         const int q = k0 / 8 + lchunk;
         uint32_t bits;
         if (P.inj_feat == nullptr)
@@ -161,11 +170,11 @@ proj_simt_kernel(const SimtParams P) {
   }
 }
 
-cudaError_t launch_proj_simt(const Weights& w, const Plan& p, const MaskSpec& m, const float* H,
+cudaError_t launch_proj_simt(const Weights& w, const Plan& p, const MaskSpec& m, const void* H, int h_f16,
                              float* logits, float* scores, cudaStream_t st, int* launches) {
   for (int s = 0; s < w.S; ++s) {
     SimtParams P;
-    P.H = H;
+    P.H = H; P.h_f16 = h_f16;
     P.WT = w.d_wt + (size_t)s * L * 256;
     P.bv = w.d_bv + s * D; P.bu = w.d_bu + s * D;
     P.ww = w.d_ww; P.bw = w.d_bw; P.cls = w.d_cls;

@@ -91,7 +91,8 @@ constexpr uint32_t TM_A = 0, TM_B = 96, TM_BUF_STRIDE = 160;
 static_assert(NBUF * TM_BUF_STRIDE <= TMEM_COLS, "TMEM columns");
 
 struct ProjParams {
-  const float* H;          // [R][512] fp32 packed features
+  const void* H;           // [R][512] packed features, fp32 or (h_f16) fp16
+  int h_f16;
   const uint8_t* wmain;    // this set: [2][8][17 KB]
   const TileDesc* tiles;
   float* logits;           // [T][C][Rp]
@@ -429,11 +430,15 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         for (int si = 0; si < TEAM_SLICES; ++si) {
           uint4 packed = make_uint4(0, 0, 0, 0);
           if (trow < td.nrows) {
-            const float4* src = reinterpret_cast<const float4*>(
-                P.H + (size_t)(td.row0 + trow) * L + (TEAMS * si + team) * KSLICE + chunk * 8);
-            const float4 a = __ldg(src), b = __ldg(src + 1);
-            packed.x = pack_half2(a.x, a.y); packed.y = pack_half2(a.z, a.w);
-            packed.z = pack_half2(b.x, b.y); packed.w = pack_half2(b.z, b.w);
+            const size_t e0 = (size_t)(td.row0 + trow) * L + (TEAMS * si + team) * KSLICE + chunk * 8;
+            if (P.h_f16) {                                   // fp16 features: the tile is already in MMA precision
+              packed = __ldg(reinterpret_cast<const uint4*>(static_cast<const __half*>(P.H) + e0));
+            } else {
+              const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(P.H) + e0);
+              const float4 a = __ldg(src), b = __ldg(src + 1);
+              packed.x = pack_half2(a.x, a.y); packed.y = pack_half2(a.z, a.w);
+              packed.z = pack_half2(b.x, b.y); packed.w = pack_half2(b.z, b.w);
+            }
           }
           hreg[si][i] = packed;
         }
@@ -651,7 +656,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
   }
 }
 
-cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const float* H,
+cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const void* H, int h_f16,
                            float* logits, float* scores, float* dbg, cudaStream_t st, int* launches) {
   using KernelFn = void (*)(ProjParams);
   // [rounds 10 / 7][mask source][heads per launch]
@@ -692,7 +697,7 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
   if (n_pairs < 1) return cudaSuccess;
   for (int s = 0; s < w.S; ++s) {
     ProjParams P;
-    P.H = H;
+    P.H = H; P.h_f16 = h_f16;
     P.wmain = w.d_wmain + (size_t)s * 2 * NSLICE * SLICE_BYTES_W;
     P.tiles = p.d_tiles;
     P.logits = logits; P.scores = scores;

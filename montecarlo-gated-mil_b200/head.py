@@ -181,7 +181,7 @@ def mc_head(weights: HeadWeights, H: torch.Tensor, T: int, seed: int = 0,
             philox_rounds: int = 10) -> MCHeadResult:
     """Run T MC-dropout passes of the GA-MIL head on packed features.
 
-    H            (R, 512) fp32 CUDA, contiguous: one bag (cu_seqlens=None) or a packed batch
+    H            (R, 512) fp32 (or fp16) CUDA, contiguous: one bag (cu_seqlens=None) or a packed batch
     cu_seqlens   bag boundaries (host ints), len n_bags+1
     bag_ids      global id of each bag (keys the Philox masks); default 0..n_bags-1 (+ bag_offset)
     keep_f_bits  optional injected feature keep-mask, uint32/int32 (T, R, 16) CUDA
@@ -193,8 +193,8 @@ def mc_head(weights: HeadWeights, H: torch.Tensor, T: int, seed: int = 0,
         raise RuntimeError("mc_head: H must be a CUDA tensor (no CPU fallback)")
     if H.dim() != 2 or H.shape[1] != L_FEAT:
         raise ValueError(f"mc_head: H must be (R, {L_FEAT}), got {tuple(H.shape)}")
-    if H.dtype != torch.float32 or not H.is_contiguous():
-        raise ValueError("mc_head: H must be contiguous float32")
+    if H.dtype not in (torch.float32, torch.float16) or not H.is_contiguous():
+        raise ValueError("mc_head: H must be contiguous float32 (or float16: features that already are half precision)")
     if H.device != weights.device:
         raise ValueError("mc_head: H and the weights live on different devices")
     if impl not in _lib.IMPLS:
@@ -233,11 +233,12 @@ def mc_head(weights: HeadWeights, H: torch.Tensor, T: int, seed: int = 0,
         am = torch.empty((C_, R), dtype=torch.float32, device=dev)
         aq = torch.empty((C_, R), dtype=torch.float32, device=dev)
         ws = _get_workspace(plan.ws_bytes, dev)
-        code = lib.mcmil_head_forward(weights._h, plan._h, _ptr(H), int(t_offset), int(bag_offset),
-                                      int(seed) & 0xFFFFFFFFFFFFFFFF, int(philox_rounds), float(p_f), float(p_a),
-                                      _ptr(keep_f_bits), _ptr(keep_a_bits), _lib.IMPLS[impl],
-                                      _ptr(Y), _ptr(A), _ptr(pm), _ptr(pq), _ptr(am), _ptr(aq),
-                                      _ptr(ws), ws.numel(), _stream_ptr(dev))
+        fwd = lib.mcmil_head_forward if H.dtype == torch.float32 else lib.mcmil_head_forward_f16
+        code = fwd(weights._h, plan._h, _ptr(H), int(t_offset), int(bag_offset),
+                   int(seed) & 0xFFFFFFFFFFFFFFFF, int(philox_rounds), float(p_f), float(p_a),
+                   _ptr(keep_f_bits), _ptr(keep_a_bits), _lib.IMPLS[impl],
+                   _ptr(Y), _ptr(A), _ptr(pm), _ptr(pq), _ptr(am), _ptr(aq),
+                   _ptr(ws), ws.numel(), _stream_ptr(dev))
         _lib.check(code, "mcmil_head_forward")
         launches = int(lib.mcmil_last_launch_count())
     finally:

@@ -316,6 +316,24 @@ def test_module_forward_eval_fused_matches_torch_path(mm):
         assert m(x)[0].requires_grad                  # training keeps the torch graph
 
 
+@pytest.mark.parametrize("impl", IMPLS)
+def test_fp16_features_entry_is_bit_identical(mm, impl):
+    """mcmil_head_forward_f16: half-precision features give exactly the results of the same values passed as fp32
+    (the tensor-core path rounds to fp16 anyway; the fp32 path converts exactly)."""
+    dev = torch.device("cuda")
+    sd = G.make_weights(9, 2, False)
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
+    lens = [130, 77, 1]
+    cu = np.concatenate([[0], np.cumsum(lens)])
+    H16 = torch.from_numpy(np.concatenate([G.make_features(70 + i, n) for i, n in enumerate(lens)])).to(dev).half()
+    a = mm.mc_head(w, H16, 6, seed=4, cu_seqlens=cu, return_attention=True, impl=impl)
+    b = mm.mc_head(w, H16.float(), 6, seed=4, cu_seqlens=cu, return_attention=True, impl=impl)
+    for x, y in ((a.Y, b.Y), (a.A, b.A), (a.attn_mean, b.attn_mean), (a.attn_m2, b.attn_m2), (a.prob_m2, b.prob_m2)):
+        assert torch.equal(x, y)
+    with pytest.raises(ValueError):
+        mm.mc_head(w, H16.double(), 6, seed=4, cu_seqlens=cu)
+
+
 def test_runner_equals_mc_head(mm):
     """MCHeadRunner (pre-created plan / outputs, one C-ABI call per bag) returns bit-identical results."""
     dev = torch.device("cuda")
