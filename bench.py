@@ -260,9 +260,14 @@ def run_ours(args):
     peak_sust = float(peaks.get("bf16_tflops_sustained", 1400.0))
     k_ms = prof_ms.value / max(prof_k.value, 1)
     achieved = (flops_step / S) / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "proj_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "peak_source": "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback",
-                "frac_of_sustained": achieved / peak_sust, "kernel_ms": k_ms, "kernel_launches": prof_k.value,
+    # Peak: MEASURED_PEAKS.json holds a burst figure (one cuBLAS bf16 GEMM timed alone) and a sustained one (GEMMs back
+    # to back for seconds).  The projection kernel is timed inside a long step (K steps of ~6 ms back to back, each
+    # ~96 % this kernel), so the sustained figure is the roofline; the fraction of the burst figure is reported too.
+    roofline = {"bound": "tensor", "kernel": "proj_tc_kernel", "achieved": achieved, "peak": peak_sust, "unit": "TFLOP/s",
+                "frac": achieved / peak_sust,
+                "peak_source": ("measured (MEASURED_PEAKS.json bf16 sustained: kernel timed inside a long step)" if peaks
+                                else "fallback"),
+                "peak_burst": peak, "frac_of_burst": achieved / peak, "kernel_ms": k_ms, "kernel_launches": prof_k.value,
                 "kernel_share_of_step": prof_ms.value / ms_total if ms_total > 0 else None, "traffic": None}
     # DRAM traffic per launch of that kernel, from the committed ncu capture of this very configuration
     # (profiles/r1_traffic.json; ncu is never attached to a timed run)
@@ -294,7 +299,7 @@ def run_ours(args):
         ms7 = f0.elapsed_time(f1)
         k7 = p7_ms.value / max(p7_k.value, 1)
         philox7 = {"bags_per_s_this_rank": n_bags * args.steps / (ms7 / 1e3),
-                   "kernel_ms": k7, "roofline_frac": (flops_step / S) / (k7 * 1e-3) / 1e12 / peak if k7 > 0 else None}
+                   "kernel_ms": k7, "roofline_frac": (flops_step / S) / (k7 * 1e-3) / 1e12 / peak_sust if k7 > 0 else None}
 
     # ---- e2e: pinned-host features in, results out, through the public API, inside the timed region
     e2e, e2e_f16 = None, None
