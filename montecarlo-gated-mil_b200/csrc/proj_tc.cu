@@ -303,8 +303,13 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     // (addresses / descriptors in uniform registers: a lane-0-only loop makes ptxas emit ELECT +
     // R2UR chains per MMA); one elected lane issues the tcgen05 ops.
     if (rank == 0) {
+#ifdef MCMIL_EXP_NSPLIT      // timing experiment only (results are garbage): other N splits of the two MMAs per K-step
+      constexpr uint32_t IDESC_A = umma_idesc_f16(128, MCMIL_EXP_NSPLIT);
+      constexpr uint32_t IDESC_B = umma_idesc_f16(128, 272 - MCMIL_EXP_NSPLIT);
+#else
       constexpr uint32_t IDESC_A = umma_idesc_f16(128, 2 * W_ROWS_A);
       constexpr uint32_t IDESC_B = umma_idesc_f16(128, 2 * W_ROWS_B);
+#endif
       const uint32_t q = (uint32_t)(warp - MMA_WARP);          // this warp issues the samples tc = q (mod NMMA)
       uint32_t mbuf = q % NBUF;                                 // ... into TMEM accumulator buffer tc % NBUF
       uint32_t mslot = (q * TEAM_SLICES) % TEAM_SLOTS;          // ring slot (per team) of the sample's first slice
