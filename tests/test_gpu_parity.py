@@ -193,6 +193,66 @@ def test_config2_tcgen05_vs_fp32_and_properties(mm, shared):
     assert not torch.equal(a.Y, a3.Y)
 
 
+def test_config3_ragged_batch_full_size_properties(mm):
+    """BASELINE config 3 at full size (256 bags, N ~ U{200..3000}, T=50, ~410 k packed rows): size-independent
+    properties of the tensor-core path on the whole batch, tensor-core vs fp32 path on a slice of its bags, and
+    independence of a bag's result from the batch it is packed into (masks are keyed by the global bag id)."""
+    dev = torch.device("cuda")
+    lens = [int(v) for v in np.random.default_rng(0).integers(200, 3001, 256)]
+    cu = np.concatenate([[0], np.cumsum(lens)])
+    T = 50
+    sd = G.make_weights(33, 2, True)
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
+    g = torch.Generator(device=dev).manual_seed(7)
+    H = torch.relu(torch.randn(int(cu[-1]), 512, generator=g, device=dev))
+    r = mm.mc_head(w, H, T, seed=11, cu_seqlens=cu)
+    assert torch.isfinite(r.Y).all() and r.Y.shape == (256, T, 2)
+    seg = torch.from_numpy(np.repeat(np.arange(256), lens)).to(dev)
+    sums = torch.zeros(2, 256, device=dev).index_add_(1, seg, r.attn_mean)
+    assert (sums - 1).abs().max().item() < 2e-4                       # mean attention of every bag sums to one
+    assert (r.prob_mean.sum(-1) - 1).abs().max().item() < 1e-5
+    assert (r.attn_m2 >= 0).all() and (r.prob_m2 >= 0).all()
+    assert (r.probs().mean(1) - r.prob_mean).abs().max().item() < 1e-6
+    r2 = mm.mc_head(w, H, T, seed=11, cu_seqlens=cu)
+    assert torch.equal(r.Y, r2.Y) and torch.equal(r.attn_m2, r2.attn_m2)   # run-to-run determinism
+    # bags 100..103 on their own, with their global ids: same numbers as inside the big batch
+    b0, b1 = 100, 104
+    sub = mm.mc_head(w, H[cu[b0]:cu[b1]].contiguous(), T, seed=11, cu_seqlens=cu[b0:b1 + 1] - cu[b0],
+                     bag_ids=list(range(b0, b1)))
+    assert torch.equal(sub.Y, r.Y[b0:b1]) and torch.equal(sub.attn_mean, r.attn_mean[:, cu[b0]:cu[b1]])
+    ref = mm.mc_head(w, H[cu[b0]:cu[b1]].contiguous(), T, seed=11, cu_seqlens=cu[b0:b1 + 1] - cu[b0],
+                     bag_ids=list(range(b0, b1)), impl="simt_fp32")
+    assert (sub.probs() / ref.probs() - 1).abs().max().item() < PROB_RTOL
+    assert (sub.attn_mean - ref.attn_mean).abs().max().item() < ATTN_ATOL
+    assert (sub.attn_mean / ref.attn_mean - 1).abs().max().item() < 5e-3
+
+
+def test_config4_large_bag_properties(mm):
+    """BASELINE config 4 shape (one bag, N=16384) at a reduced sample count: tensor-core vs fp32 path, and the
+    MC-sample split (two shards of the global sample range, merged with the additive Welford form) against the
+    single call."""
+    from mcmil_b200 import distributed as MD
+    dev = torch.device("cuda")
+    N, T = 16384, 24
+    sd = G.make_weights(35, 2, True)
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
+    g = torch.Generator(device=dev).manual_seed(9)
+    H = torch.relu(torch.randn(N, 512, generator=g, device=dev))
+    a = mm.mc_head(w, H, T, seed=3)
+    b = mm.mc_head(w, H, T, seed=3, impl="simt_fp32")
+    assert (a.probs() / b.probs() - 1).abs().max().item() < PROB_RTOL
+    assert (a.attn_mean - b.attn_mean).abs().max().item() < ATTN_ATOL
+    assert (a.attn_mean / b.attn_mean - 1).abs().max().item() < 5e-3
+    assert (a.attn_mean.sum(-1) - 1).abs().max().item() < 2e-4
+    parts = [mm.mc_head(w, H, 12, seed=3, t_offset=t0) for t0 in (0, 12)]
+    assert torch.equal(torch.cat([p.Y for p in parts], 1), a.Y)        # same global samples, bit for bit
+    packed = sum(MD.welford_pack(torch.cat([p.attn_mean.reshape(-1), p.prob_mean.reshape(-1)]),
+                                 torch.cat([p.attn_m2.reshape(-1), p.prob_m2.reshape(-1)]), 12) for p in parts)
+    mean, m2 = MD.welford_unpack(packed, 2 * N + 2)
+    assert (mean[:2 * N].view(2, N) - a.attn_mean).abs().max().item() < 1e-7
+    assert (m2[:2 * N].view(2, N) - a.attn_m2).abs().max().item() < 1e-6 * max(1.0, a.attn_m2.abs().max().item()) + 1e-9
+
+
 def test_sample_sharding_equals_single_call(mm):
     """MC-sample split (config 4 mechanics on one GPU): two half-calls with t_offset + the additive
     Welford merge reproduce the single call — masks are keyed by the global sample index."""
