@@ -18,6 +18,15 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// exp / reciprocal without the range fix-ups of __expf / __fdividef (arguments here are <= 0 resp. small positive
+// integers; a denormal result flushing to zero is irrelevant): 2 instructions instead of 6
+__device__ __forceinline__ float fast_exp(float x) {
+  float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f)); return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+
 constexpr int ROW_THREADS = 256;
 
 // one CTA per (bag, t, c) row: rowstat = (max, 1/sum exp), Y[bag][t][c] = sum_n softmax_n * score
@@ -48,7 +57,7 @@ softmax_rows_kernel(const float* __restrict__ logits, const float* __restrict__ 
 
   float z = 0.f, y = 0.f;
   for (int i = threadIdx.x; i < n; i += ROW_THREADS) {
-    const float e = __expf(lg[i] - m);
+    const float e = fast_exp(lg[i] - m);
     z += e;
     y = fmaf(e, sc[i], y);
   }
@@ -98,7 +107,7 @@ softmax_rows_warp_kernel(const float* __restrict__ logits, const float* __restri
   float z = 0.f, y = 0.f;
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
-    const float e = __expf(v[k] - m);                        // exp(-inf) = 0 for the padding
+    const float e = fast_exp(v[k] - m);                      // exp(-inf) = 0 for the padding
     z += e;
     y = fmaf(e, w[k], y);
   }
@@ -146,7 +155,7 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
     int b[COL_VEC];
 #pragma unroll
     for (int k = 0; k < COL_VEC; ++k) b[k] = row2bag[min(g0 + k, R - 1)];
-    const bool one_bag = b[0] == b[COL_VEC - 1];
+    const bool warp_mixed = __any_sync(0xffffffffu, b[0] != b[COL_VEC - 1]);
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(&s_lg[0][0]);
     for (int t0 = 0; t0 < T; t0 += COL_CHUNK_T) {
       const int nt = min(COL_CHUNK_T, T - t0);
@@ -173,15 +182,16 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
           rs[0] = __ldg(rs_row + r);
 #pragma unroll
           for (int k = 1; k < COL_VEC; ++k) rs[k] = rs[0];
-          if (!one_bag) {                                    // a bag boundary inside this lane's four rows (rare)
+          if (warp_mixed) {                                  // a bag boundary inside this warp's 128 rows (warp-uniform branch)
 #pragma unroll
-            for (int k = 1; k < COL_VEC; ++k) rs[k] = __ldg(rowstat + ((size_t)c * n_bags + b[k]) * T + t0 + r);
+            for (int k = 1; k < COL_VEC; ++k)
+              if (b[k] != b[0]) rs[k] = __ldg(rowstat + ((size_t)c * n_bags + b[k]) * T + t0 + r);
           }
           ++cnt;
-          const float inv_cnt = __fdividef(1.0f, (float)cnt);
+          const float inv_cnt = fast_rcp((float)cnt);
 #pragma unroll
           for (int k = 0; k < COL_VEC; ++k) {
-            const float a = __expf(lg[k] - rs[k].x) * rs[k].y;
+            const float a = fast_exp(lg[k] - rs[k].x) * rs[k].y;
             if constexpr (HAS_A) {
               if (g0 + k < R) A[((size_t)(t0 + r) * C + c) * R + g0 + k] = a;
             }
