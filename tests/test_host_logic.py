@@ -31,6 +31,31 @@ def test_no_cpu_fallback():
     m = mm.MultiHeadGatedAttentionMIL(pretrained=False)
     with pytest.raises(RuntimeError):
         m.mc_inference(torch.zeros(1, 2, 3, 32, 32), N=2, device="cpu")
+    # every other entry point refuses host tensors as well: nothing routes around the CUDA library
+    with pytest.raises(RuntimeError):
+        mm.aux_pairwise_loss(torch.zeros(2, 2, 8), True)
+    with pytest.raises(RuntimeError):
+        m.forward_eval_fused(torch.zeros(1, 2, 3, 32, 32))
+    with pytest.raises(RuntimeError):
+        mm.mc_head(None, torch.zeros(4, 512), 2)
+
+
+def test_eval_forward_on_cpu_is_the_plain_torch_graph():
+    """forward() only routes through the fused head for CUDA inputs in eval mode under no_grad; on the host it is
+    the reference's torch graph (the training path), including the auxiliary loss (model.py:243-248)."""
+    import mcmil_b200 as mm
+    from oracle import gamil_oracle as G
+    sd = G.make_weights(3, 2, True)
+    m = mm.MultiHeadGatedAttentionMIL(pretrained=False)
+    m.feature_extractor = torch.nn.Flatten()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    m.eval()
+    H = G.make_features(11, 40)
+    with torch.no_grad():
+        Y, A, aux = m(torch.from_numpy(H).view(1, 40, 512, 1, 1), targets=torch.tensor([1]))
+    o = G.forward_oracle(sd, H)
+    assert np.abs(Y[0].numpy() - o["Y"]).max() < 5e-6 and np.abs(A[0].numpy() - o["A"]).max() < 2e-7
+    assert abs(float(aux) - float(G.aux_pairwise_loss(o["A"][1], o["A"][0], True))) < 1e-6
 
 
 def test_module_state_dict_matches_reference_schema():
