@@ -77,6 +77,33 @@ def test_feature_mask_stream_statistics():
     assert np.abs(per_l - q).max() < 6 * np.sqrt(q * (1 - q) / (T * N))
 
 
+def test_philox_masks_are_statistically_equivalent_to_torch_dropout():
+    """The counter-based masks cannot reproduce torch's generator stream; what must hold is that the MC
+    statistics agree in distribution.  Same head, same bag: T samples with the reference's native torch dropout
+    (torch port, bit-identical to the reference for a seed) vs T samples with the Philox masks — class-probability
+    mean and per-patch attention mean agree within the Monte-Carlo error of the two estimates."""
+    import torch
+    from oracle import torch_port as TP
+    N, T, C = 48, 1500, 2
+    sd = G.make_weights(21, C, True, peaky=3.0)
+    H = G.make_features(77, N)
+    torch.manual_seed(5)
+    Yt, At = TP.mc_head_torch(TP.sd_to_torch(sd), torch.from_numpy(H), T, 0.1, 0.1)
+    a = G.finish_stats(Yt.reshape(T, C).double().numpy(), At.reshape(T, C, N).double().numpy())
+    kf = PX.feature_keep(99, 0, 0, T, N, 0.1)
+    ka = PX.attn_keep(99, 0, 0, T, N, C, 0.1)
+    b = G.mc_head_oracle(sd, H, kf, ka, 0.1, 0.1)
+    # z-scores of the difference of two independent sample means
+    se_p = np.sqrt((a["prob_m2"] + b["prob_m2"]) / (T - 1) / T)
+    assert (np.abs(a["prob_mean"] - b["prob_mean"]) / se_p).max() < 4.5
+    se_a = np.sqrt((a["attn_m2"] + b["attn_m2"]) / (T - 1) / T)
+    z = np.abs(a["attn_mean"] - b["attn_mean"]) / se_a
+    assert z.max() < 5.0 and (z ** 2).mean() < 1.6          # ~chi-square with mean 1 over the 96 (head, patch) cells
+    # and the spread itself matches: ratio of the variances of the probability samples
+    ratio = (b["prob_m2"] / a["prob_m2"])
+    assert np.all(ratio > 0.8) and np.all(ratio < 1.25)
+
+
 def test_pack_bits_roundtrip():
     rng = np.random.default_rng(0)
     k = (rng.random((3, 5, 77)) < 0.9).astype(np.uint8)
