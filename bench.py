@@ -5,22 +5,31 @@
 
 Workload at the default (`config2`, BASELINE.json configs[1]): bags of N=1024 patches x 512-d
 features, T=100 MC-dropout passes, 2 heads, shared attention.  A *step* is one pass of the hot
-path (feature packing -> tcgen05 projection -> softmax rows -> Welford columns) over one packed
-batch of `--bags-per-step` such bags (256 by default = 512 MB of fp32 features per GPU, larger
-than the 126 MB L2, so no L2 flush is needed between timed steps).  N > 1: every rank owns its
-own batch (bags are independent units: weak scaling, no data-path collective).
+path (tcgen05 projection -> softmax rows -> Welford columns) over one packed batch of
+`--bags-per-step` such bags (256 by default = 512 MB of fp32 features per GPU, larger than the
+126 MB L2, so no L2 flush is needed between timed steps).  N > 1: every rank owns its own batch
+(bags are independent units: weak scaling, no data-path collective).
 
 Prints ONE JSON line (see the task contract): `value` = bags/s with inputs resident in HBM,
 `e2e` = the same metric through the public Python API with pinned-host features copied in and
 results copied out inside the timed region, `roofline` for the projection kernel (CUDA events
-around it, live), `cpu_baseline` = the torch-CPU port of the reference head on this host.
-`--impl reference` times that port alone (the reference itself is Python and stays in the
-build container; oracle/torch_port.py is bit-identical to it for the same seed).
+around it, live), `cpu_baseline` = the reference's CPU path on this host.  Extras of the same line
+(all measured in this run, every N): `single_bag` (the reference's bs == 1 call pattern),
+`separate` (shared_attention=False, the reference's YAML default), `config3` (256 ragged bags,
+LPT bag sharding, strong scaling, no collective), `config4` (one bag of 16384 patches, T=1000, MC
+samples sharded over the ranks + ONE NCCL all-reduce of the Welford partials, with an on-device
+check of the merged statistics against a single-rank run of the same global samples).
+
+`--impl reference` times the reference's own CPU implementation: `baseline/_ref/model.py` (the
+unmodified reference module, placed there by `__graft_entry__.build()` when `/root/reference`
+exists) or `/root/reference/model.py`, else the torch-CPU port `oracle/torch_port.py`
+(bit-identical to the reference for the same seed, tests/golden/make_golden.py).
 """
 from __future__ import annotations
 
 import argparse
 import ctypes
+import importlib.util
 import json
 import os
 import sys
@@ -124,20 +133,62 @@ def workload(name, bags_per_step, seed):
 
 
 # =============================================================================================== reference arm
+def load_reference_module():
+    """The reference's own model.py: baseline/_ref (travels to the GPU box) or /root/reference (build container)."""
+    for path in (os.path.join(ROOT, "baseline", "_ref", "model.py"), "/root/reference/model.py"):
+        if os.path.exists(path):
+            try:
+                spec = importlib.util.spec_from_file_location("_mcmil_reference_model", path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                return mod, path
+            except Exception as e:  # noqa: BLE001  (e.g. torchvision missing): fall back to the port
+                print(f"bench: could not import {path}: {e!r}", file=sys.stderr)
+    return None, None
+
+
+class CpuHead:
+    """One bag through the reference's CPU path: the unmodified reference module when it is present
+    (kind "reference": model.py:256-328 with `feature_extractor = nn.Flatten()` so the features go in
+    directly, as SURVEY §8c), else the torch port (kind "port")."""
+
+    def __init__(self, shared, threads):
+        torch.set_num_threads(threads)
+        self.sd = make_state_dict(0, shared)
+        self.mod, self.path = load_reference_module()
+        self.kind = "reference" if self.mod is not None else "port"
+        if self.mod is not None:
+            m = self.mod.MultiHeadGatedAttentionMIL(pretrained=False, shared_attention=shared)
+            m.feature_extractor = torch.nn.Flatten()
+            missing, unexpected = m.load_state_dict(self.sd, strict=False)
+            assert not unexpected and all(k.startswith("feature_extractor") for k in missing), (missing, unexpected)
+            self.model = m
+        else:
+            from oracle import torch_port as TP
+            self.TP = TP
+
+    def run(self, H, T):
+        if self.mod is not None:
+            return self.model.mc_inference(H.view(1, H.shape[0], L, 1, 1), N=T, device="cpu")
+        return self.TP.mc_head_torch(self.sd, H, T, 0.1, 0.1)        # native torch dropout: the reference's true path
+
+    def describe(self):
+        return ("unmodified reference module %s (mc_inference, device='cpu', native dropout)" % os.path.relpath(self.path, ROOT)
+                if self.mod is not None else "torch-CPU port of model.py:280-316 (oracle/torch_port.py, native dropout)")
+
+
 def cpu_head_bags_per_s(n_bags, N, T, shared, threads, warmup=1):
-    from oracle import torch_port as TP
-    torch.set_num_threads(threads)
-    sd = make_state_dict(0, shared)
+    head = CpuHead(shared, threads)
     g = torch.Generator().manual_seed(1)
     Hs = [torch.relu(torch.randn(N, L, generator=g)) for _ in range(min(n_bags, 4))]
     for i in range(warmup):
-        TP.mc_head_torch(sd, Hs[i % len(Hs)], T, 0.1, 0.1)
+        head.run(Hs[i % len(Hs)], T)
     times = []
     for i in range(n_bags):
         t0 = time.perf_counter()
-        TP.mc_head_torch(sd, Hs[i % len(Hs)], T, 0.1, 0.1)      # native torch dropout: the reference's true path
+        head.run(Hs[i % len(Hs)], T)
         times.append(time.perf_counter() - t0)
-    return n_bags / sum(times), times
+    return n_bags / sum(times), times, head
 
 
 def run_reference(args):
@@ -149,18 +200,18 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     T_run = T if args.workload != "config4" else 25     # the reference cannot materialise (1000,1,16384,512)
     t0 = time.perf_counter()
-    bps, times = cpu_head_bags_per_s(args.steps, N, T_run, not args.separate, cores, warmup=args.warmup)
+    bps, times, head = cpu_head_bags_per_s(args.steps, N, T_run, not args.separate, cores, warmup=args.warmup)
     if T_run != T:
         bps *= T_run / T
     ms = 1e3 * sum(times) / len(times) * (T / T_run)
-    sample = f"{args.steps} bag(s) of N={N}, T={T_run}, one per step, torch-CPU port of model.py:280-316 with native dropout"
+    sample = f"{args.steps} bag(s) of N={N}, T={T_run}, one per step: {head.describe()}, {cores} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": bps, "unit": "bags/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: N={N} patches x 512, T={T}, 2 heads, "
                                f"{'separate' if args.separate else 'shared'} attention; 1 bag per step on host cores"},
-        "cpu_baseline": {"value": bps, "unit": "bags/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": bps, "unit": "bags/s", "cores": cores, "kind": head.kind, "sample": sample},
         "e2e": {"value": bps, "unit": "bags/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
@@ -187,6 +238,52 @@ def run_ours(args):
     from mcmil_b200 import distributed as MD
     lib = _lib.load()
 
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    peak_burst = float(peaks.get("bf16_tflops", 1590.0))
+    peak_sust = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step_fn, steps, warm, profile=False):
+        """`warm` untimed + `steps` timed calls of step_fn(i); CUDA events, barrier + synchronize on both sides,
+        max over ranks.  profile: also the summed device time of the projection launches (library events)."""
+        for i in range(warm):
+            step_fn(i)
+        barrier()
+        if profile:
+            _lib.check(lib.mcmil_profile_begin(steps * 2), "mcmil_profile_begin")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            step_fn(1000 + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = None
+        if profile:
+            pm, pk = ctypes.c_double(0), ctypes.c_int(0)
+            _lib.check(lib.mcmil_profile_end(ctypes.byref(pm), ctypes.byref(pk)), "mcmil_profile_end")
+            prof = (pm.value, pk.value)
+        return max_over_ranks(ms), prof
+
+    # ------------------------------------------------------------------------------------------ main leg
     shared = not args.separate
     S = 1 if shared else C
     w = mm.HeadWeights(make_state_dict(0, shared), dev)
@@ -207,13 +304,8 @@ def run_ours(args):
     H = torch.relu(torch.randn(R, L, generator=g, device=dev))       # synthetic ResNet-like features (>= 0)
     n_bags = len(lens)
     flops_step = sum(flops_per_bag(n, T, S) for n in lens)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
     merged_T = [T]
+    last = [None]
 
     def step(i, rounds=None):
         r = mm.mc_head(w, H, T, seed=i, cu_seqlens=cu, bag_ids=bag_ids, t_offset=t_offset,
@@ -221,97 +313,92 @@ def run_ours(args):
         if args.workload == "config4" and world > 1:
             _, _, merged_T[0] = MD.allreduce_welford([r.attn_mean, r.prob_mean], [r.attn_m2, r.prob_m2], T,
                                                      total_count=T_job)
+        last[0] = r
         return r
 
-    for i in range(max(args.warmup, 3)):
-        res = step(i)
-    launches_per_step = res.launches
-    barrier()
     sampler = ClockSampler(local_rank)
+    warm = max(args.warmup, 3)
+    for i in range(warm):          # warm-up outside the clock sampling
+        step(i)
+    barrier()
     sampler.start()
-    _lib.check(lib.mcmil_profile_begin(args.steps), "mcmil_profile_begin")
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step(100 + i)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    prof_ms, prof_k = ctypes.c_double(0), ctypes.c_int(0)
-    _lib.check(lib.mcmil_profile_end(ctypes.byref(prof_ms), ctypes.byref(prof_k)), "mcmil_profile_end")
+    ms_total, (prof_ms, prof_k) = timed(step, args.steps, 0, profile=True)
     clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    launches_per_step = last[0].launches
     strong = args.workload in ("config3", "config4") and world > 1
     job_bags = len(all_lens) if strong else n_bags * world
     value = job_bags * args.steps / (ms_total / 1e3)
 
-    # ---- roofline of the dominant kernel (tcgen05 projection), CUDA events around its launches
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:  # noqa: BLE001
-        pass
-    peak = float(peaks.get("bf16_tflops", 1590.0))
-    peak_sust = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    k_ms = prof_ms.value / max(prof_k.value, 1)
-    achieved = (flops_step / S) / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    # ---- roofline of the dominant kernel (tcgen05 projection), CUDA events around its launches.
     # Peak: MEASURED_PEAKS.json holds a burst figure (one cuBLAS bf16 GEMM timed alone) and a sustained one (GEMMs back
-    # to back for seconds).  The projection kernel is timed inside a long step (K steps of ~6 ms back to back, each
-    # ~96 % this kernel), so the sustained figure is the roofline; the fraction of the burst figure is reported too.
-    roofline = {"bound": "tensor", "kernel": "proj_tc_kernel", "achieved": achieved, "peak": peak_sust, "unit": "TFLOP/s",
-                "frac": achieved / peak_sust,
-                "peak_source": ("measured (MEASURED_PEAKS.json bf16 sustained: kernel timed inside a long step)" if peaks
-                                else "fallback"),
-                "peak_burst": peak, "frac_of_burst": achieved / peak, "kernel_ms": k_ms, "kernel_launches": prof_k.value,
-                "kernel_share_of_step": prof_ms.value / ms_total if ms_total > 0 else None, "traffic": None}
-    # DRAM traffic per launch of that kernel, from the committed ncu capture of this very configuration
-    # (profiles/r1_traffic.json; ncu is never attached to a timed run)
-    if args.workload == "config2" and args.bags_per_step == 256 and shared and args.philox_rounds == 10:
+    # to back for seconds, power-capped).  The contract assigns the sustained figure to kernels timed inside a long
+    # step; a timed region shorter than one second is not long, so the burst figure is the denominator there.
+    k_ms = prof_ms / max(prof_k, 1)
+    achieved = (flops_step / S) / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    long_region = ms_total >= 1000.0
+    peak = peak_sust if long_region else peak_burst
+    roofline = {"bound": "tensor", "kernel": "proj_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak,
+                "peak_source": ("%s (MEASURED_PEAKS.json bf16 %s: timed region %.2f s)" % (
+                    "measured" if peaks else "fallback", "sustained" if long_region else "burst", ms_total / 1e3)),
+                "peak_burst": peak_burst, "frac_of_burst": achieved / peak_burst,
+                "peak_sustained": peak_sust, "frac_of_sustained": achieved / peak_sust,
+                "kernel_ms": k_ms, "kernel_launches": prof_k,
+                "kernel_share_of_step": prof_ms / ms_total if ms_total > 0 else None,
+                "algorithmic_flops_per_launch": flops_step / S, "traffic": None}
+    # DRAM traffic per launch of that kernel: only from an ncu capture of THIS round's binary at this very
+    # configuration (profiles/r2_traffic.json; ncu is never attached to a timed run); otherwise null.
+    if args.workload == "config2" and args.bags_per_step == 256 and shared and args.philox_rounds == 10 and world == 1:
         try:
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
                 tr = json.load(f)["config2_shared"]
             roofline["traffic"] = tr["dram_read_bytes"] + tr["dram_write_bytes"]
-            roofline["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json)"
+            roofline["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r2_traffic.json)"
             roofline["algorithmic_bytes"] = sum(tr["algorithmic_bytes"].values())
         except Exception:  # noqa: BLE001
             pass
 
+    extras_on = not args.no_extras and args.workload == "config2"
+
     # ---- the same step with Philox4x32-7 masks (optional fast mode; not the headline)
     philox7 = None
-    if args.philox_rounds == 10 and not args.no_extras:
-        for i in range(3):
-            step(i, 7)
-        barrier()
-        _lib.check(lib.mcmil_profile_begin(args.steps), "mcmil_profile_begin")
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for i in range(args.steps):
-            step(300 + i, 7)
-        f1.record()
-        barrier()
-        p7_ms, p7_k = ctypes.c_double(0), ctypes.c_int(0)
-        _lib.check(lib.mcmil_profile_end(ctypes.byref(p7_ms), ctypes.byref(p7_k)), "mcmil_profile_end")
-        ms7 = f0.elapsed_time(f1)
-        k7 = p7_ms.value / max(p7_k.value, 1)
+    if args.philox_rounds == 10 and extras_on and world == 1:
+        ms7, (p7_ms, p7_k) = timed(lambda i: step(i, 7), args.steps, 3, profile=True)
+        k7 = p7_ms / max(p7_k, 1)
         philox7 = {"bags_per_s_this_rank": n_bags * args.steps / (ms7 / 1e3),
-                   "kernel_ms": k7, "roofline_frac": (flops_step / S) / (k7 * 1e-3) / 1e12 / peak_sust if k7 > 0 else None}
+                   "kernel_ms": k7, "roofline_frac": (flops_step / S) / (k7 * 1e-3) / 1e12 / peak if k7 > 0 else None}
+
+    # ---- separate attention (shared_attention=False, the reference's config.yml default): same batch, S = 2
+    separate = None
+    if extras_on and shared:
+        w_sep = mm.HeadWeights(make_state_dict(0, False), dev)
+
+        def sep_step(i):
+            return mm.mc_head(w_sep, H, T, seed=i, cu_seqlens=cu, philox_rounds=args.philox_rounds)
+
+        steps_s = max(3, args.steps // 2)
+        ms_s, (ps_ms, ps_k) = timed(sep_step, steps_s, 3, profile=True)
+        fl = sum(flops_per_bag(n, T, C) for n in lens)
+        ks = ps_ms / max(ps_k, 1)                 # per projection launch (one per head)
+        ach = (fl / C) / (ks * 1e-3) / 1e12 if ks > 0 else 0.0
+        separate = {"bags_per_s": n_bags * world * steps_s / (ms_s / 1e3), "ms_per_step": ms_s / steps_s,
+                    "steps": steps_s, "kernel_ms_per_head_launch": ks, "kernel_launches": ps_k,
+                    "achieved_tflops": ach, "frac": ach / peak,
+                    "flop_rate_vs_shared": (ach / achieved) if achieved > 0 else None}
+        del w_sep
 
     # ---- e2e: pinned-host features in, results out, through the public API, inside the timed region
     e2e, e2e_f16 = None, None
 
     def measure_e2e(dtype):
         chunk_bags = max(1, min(n_bags, args.e2e_chunk))
+        n_streams = args.e2e_streams
         H_host = torch.empty((R, L), dtype=dtype).pin_memory()
         H_host.copy_(H.to(dtype).cpu())
-        streams = [torch.cuda.Stream(dev) for _ in range(2)]
+        streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
         n_chunks = (n_bags + chunk_bags - 1) // chunk_bags
         max_rows = max(int(cu[min(n_bags, (k + 1) * chunk_bags)] - cu[k * chunk_bags]) for k in range(n_chunks))
-        dbuf = [torch.empty((max_rows, L), dtype=dtype, device=dev) for _ in range(2)]
+        dbuf = [torch.empty((max_rows, L), dtype=dtype, device=dev) for _ in range(n_streams)]
         # results land in flat pinned buffers (one per chunk): every D2H copy is a single contiguous
         # cudaMemcpyAsync (a strided pinned destination makes torch stage + synchronise, which
         # serialises the whole pipeline)
@@ -331,9 +418,9 @@ def run_ours(args):
             for k in range(n_chunks):
                 b0, b1 = k * chunk_bags, min(n_bags, (k + 1) * chunk_bags)
                 r0, r1 = int(cu[b0]), int(cu[b1])
-                s = streams[k % 2]
+                s = streams[k % n_streams]
                 with torch.cuda.stream(s):
-                    hb = dbuf[k % 2][: r1 - r0]
+                    hb = dbuf[k % n_streams][: r1 - r0]
                     hb.copy_(H_host[r0:r1], non_blocking=True)
                     r = mm.mc_head(w, hb, T, seed=i, cu_seqlens=cu[b0:b1 + 1] - cu[b0],
                                    bag_ids=None if bag_ids is None else bag_ids[b0:b1], bag_offset=b0,
@@ -354,65 +441,198 @@ def run_ours(args):
         for i in range(args.steps):
             e2e_step(200 + i)
         torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(time.perf_counter() - t0)
         return {"value": job_bags * args.steps / dt, "unit": "bags/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "chunk_bags": chunk_bags, "streams": 2,
-                "api": "mcmil_b200.mc_head on pinned-host %s features (copy in, compute, copy out, pipelined over 2 streams)"
-                       % ("float32" if dtype == torch.float32 else "float16")}
+                "d2h_bytes_per_step": d2h, "chunk_bags": chunk_bags, "streams": n_streams,
+                "h2d_gbs_per_gpu": h2d * args.steps / dt / 1e9,
+                "api": "mcmil_b200.mc_head on pinned-host %s features (copy in, compute, copy out, pipelined over %d streams)"
+                       % ("float32" if dtype == torch.float32 else "float16", n_streams)}
 
     if not args.no_e2e:
         e2e = measure_e2e(torch.float32)                 # the reference's feature dtype: the e2e number of record
-        if not args.no_extras:
+        if extras_on:
             e2e_f16 = measure_e2e(torch.float16)         # features handed over in half precision (same results)
+            # the copy alone: what the host link gives this rank while all ranks copy at once (the e2e limiter)
+            hp = torch.empty((64 << 20) // 4, dtype=torch.float32).pin_memory()
+            dp = torch.empty_like(hp, device=dev)
+            for _ in range(2):
+                dp.copy_(hp, non_blocking=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(8):
+                dp.copy_(hp, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            e2e["h2d_copy_only_gbs_per_gpu"] = 8 * hp.numel() * 4 / max_over_ranks(time.perf_counter() - t0) / 1e9
+            del hp, dp
 
-    # ---- single-bag call latency / back-to-back throughput (the reference's bs=1 usage)
+    # ---- single-bag call latency / back-to-back throughput (the reference's bs == 1 serving loop, infer.py:187-196)
     single = None
-    if args.workload == "config2" and rank == 0 and not args.no_extras:
+    if extras_on and rank == 0:
         nb = min(n_bags, 128)
-        for i in range(10):
-            mm.mc_head(w, H[(i % nb) * 1024:(i % nb + 1) * 1024], T, seed=i)
-        torch.cuda.synchronize(dev)
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 200
-        s0.record()
-        for i in range(reps):
-            mm.mc_head(w, H[(i % nb) * 1024:(i % nb + 1) * 1024], T, seed=i)
-        s1.record()
-        torch.cuda.synchronize(dev)
-        per = s0.elapsed_time(s1) / reps
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def loop(fn):
+            for i in range(20):
+                fn(i)
+            torch.cuda.synchronize(dev)
+            s0.record()
+            for i in range(reps):
+                fn(i)
+            s1.record()
+            torch.cuda.synchronize(dev)
+            return s0.elapsed_time(s1) / reps
+
+        per = loop(lambda i: mm.mc_head(w, H[(i % nb) * 1024:(i % nb + 1) * 1024], T, seed=i))
         single = {"us_per_bag_back_to_back": per * 1e3, "bags_per_s": 1e3 / per, "calls": reps}
         runner = mm.MCHeadRunner(w, 1024, T)           # same call with plan / outputs created once
+        per = loop(lambda i: runner.run(H[(i % nb) * 1024:(i % nb + 1) * 1024], seed=i))
+        f1 = flops_per_bag(1024, T, S)
+        single.update({"runner_us_per_bag": per * 1e3, "runner_bags_per_s": 1e3 / per,
+                       "launches_per_bag": int(lib.mcmil_last_launch_count()),
+                       "achieved_tflops": f1 / (per * 1e-3) / 1e12, "frac_of_burst": f1 / (per * 1e-3) / 1e12 / peak_burst,
+                       "roofline_us": f1 / (peak_burst * 1e12) * 1e6})
+        # one isolated call (device time of a single call with an idle GPU before it)
+        iso = []
         for i in range(10):
-            runner.run(H[(i % nb) * 1024:(i % nb + 1) * 1024], seed=i)
-        torch.cuda.synchronize(dev)
-        s0.record()
-        for i in range(reps):
-            runner.run(H[(i % nb) * 1024:(i % nb + 1) * 1024], seed=i)
-        s1.record()
-        torch.cuda.synchronize(dev)
-        per = s0.elapsed_time(s1) / reps
-        single["runner_us_per_bag"] = per * 1e3
-        single["runner_bags_per_s"] = 1e3 / per
+            torch.cuda.synchronize(dev)
+            s0.record()
+            runner.run(H[:1024], seed=i)
+            s1.record()
+            torch.cuda.synchronize(dev)
+            iso.append(s0.elapsed_time(s1) * 1e3)
+        single["isolated_call_us_median"] = sorted(iso)[len(iso) // 2]
+
+    # ---- configs 3 and 4 of BASELINE.json, strong scaling over the ranks of this run
+    def config3_leg():
+        lens3, T3 = workload("config3", 0, args.seed)
+        mine = MD.lpt_assign(lens3, world)[rank]
+        my_lens = [lens3[i] for i in mine]
+        cu3 = np.concatenate([[0], np.cumsum(my_lens)]).astype(np.int32)
+        g3 = torch.Generator(device=dev).manual_seed(77 + rank)
+        H3 = torch.relu(torch.randn(int(cu3[-1]), L, generator=g3, device=dev))
+        steps3 = max(3, min(args.steps, 10))
+        ms3, (p_ms, p_k) = timed(lambda i: mm.mc_head(w, H3, T3, seed=i, cu_seqlens=cu3, bag_ids=mine), steps3, 3,
+                                 profile=True)
+        fl_rank = sum(flops_per_bag(n, T3, S) for n in my_lens)
+        tiles = [sum(-(-n // 128) for n in [lens3[i] for i in MD.lpt_assign(lens3, world)[r]]) for r in range(world)]
+        return {"scaling": "strong", "bags": len(lens3), "T": T3, "n_gpus": world, "steps": steps3,
+                "ms_per_step": ms3 / steps3, "bags_per_s": len(lens3) * steps3 / (ms3 / 1e3),
+                "projection_ms_per_step_this_rank": p_ms / steps3,
+                "achieved_tflops_this_rank": fl_rank / (p_ms / steps3 * 1e-3) / 1e12 if p_ms > 0 else None,
+                "tiles_per_rank_min_max": [min(tiles), max(tiles)], "collective": "none (bags are independent units)"}
+
+    def config4_leg():
+        lens4, T4 = workload("config4", 0, args.seed)
+        N4 = lens4[0]
+        t0_, Tl = MD.mc_shard(T4, rank, world)
+        g4 = torch.Generator(device=dev).manual_seed(4242)           # H is replicated: same seed on every rank
+        H4 = torch.relu(torch.randn(N4, L, generator=g4, device=dev))
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        split_ms = [0.0, 0.0]
+        merged = [None]
+
+        def step4(i):
+            timing = i >= 1000
+            if timing:
+                ev[0].record()
+            r = mm.mc_head(w, H4, Tl, seed=i, t_offset=t0_)
+            if timing:
+                ev[1].record()
+            if world > 1:
+                (am, pm), (aq, pq), _ = MD.allreduce_welford([r.attn_mean, r.prob_mean], [r.attn_m2, r.prob_m2], Tl,
+                                                             total_count=T4)
+            else:
+                am, pm, aq, pq = r.attn_mean, r.prob_mean, r.attn_m2, r.prob_m2
+            if timing:
+                ev[2].record()
+                ev[2].synchronize()           # per-step split (adds a host sync per step: reported separately below)
+                split_ms[0] += ev[0].elapsed_time(ev[1])
+                split_ms[1] += ev[1].elapsed_time(ev[2])
+            merged[0] = (r, am, aq, pm, pq)
+
+        def step4_nosync(i):
+            r = mm.mc_head(w, H4, Tl, seed=i, t_offset=t0_)
+            if world > 1:
+                MD.allreduce_welford([r.attn_mean, r.prob_mean], [r.attn_m2, r.prob_m2], Tl, total_count=T4)
+
+        steps4 = max(3, min(args.steps, 10))
+        ms4, (p_ms, p_k) = timed(step4_nosync, steps4, 3, profile=True)
+        timed(step4, steps4, 0)
+        head_ms, merge_ms = split_ms[0] / steps4, split_ms[1] / steps4
+        # ---- merged statistics vs ONE rank computing all T4 samples of the same Philox stream (every rank checks)
+        seed_chk = 31337
+        step4(seed_chk)
+        r, am, aq, pm, pq = merged[0]
+        full = mm.mc_head(w, H4, T4, seed=seed_chk)
+        d_mean = float((am - full.attn_mean).abs().max())
+        d_m2 = float((aq - full.attn_m2).abs().max() / full.attn_m2.abs().max())
+        d_pm = float((pm - full.prob_mean).abs().max())
+        d_pq = float((pq - full.prob_m2).abs().max() / max(float(full.prob_m2.abs().max()), 1e-30))
+        y_equal = bool(torch.equal(r.Y, full.Y[:, t0_:t0_ + Tl]))
+        ok = d_mean <= 1e-7 and d_m2 <= 1e-4 and d_pm <= 1e-6 and d_pq <= 1e-3 and y_equal
+        flags = torch.tensor([1.0 if ok else 0.0, d_mean, d_m2, d_pm, d_pq], dtype=torch.float64, device=dev)
+        if world > 1:
+            mn = flags.clone()
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+            all_ok = bool(mn[0].item() == 1.0)
+        else:
+            all_ok = ok
+        payload = (1 + 2 * (C * N4 + C)) * 8
+        return {"scaling": "strong", "N": N4, "T": T4, "T_per_rank": Tl, "n_gpus": world, "steps": steps4,
+                "ms_per_step": ms4 / steps4, "bags_per_s": steps4 / (ms4 / 1e3),
+                "projection_ms_per_step_this_rank": p_ms / steps4,
+                "head_ms_this_rank": head_ms, "merge_ms_this_rank": merge_ms,
+                "collective": ("one NCCL all_reduce(sum) of %d bytes (fp64 additive Welford form) per step" % payload)
+                if world > 1 else "none (single rank)",
+                "merge_check": {"ok": all_ok, "ranks_checked": world,
+                                "vs": "single-rank mc_head over all T samples of the same Philox stream, same seed",
+                                "attn_mean_max_abs_diff": float(flags[1]), "attn_m2_max_diff_rel_to_max": float(flags[2]),
+                                "prob_mean_max_abs_diff": float(flags[3]), "prob_m2_max_diff_rel_to_max": float(flags[4]),
+                                "per_sample_logits_bit_equal": y_equal,
+                                "bounds": "mean 1e-7 abs, M2 1e-4 of max (fp32 Welford grouping differs), prob mean 1e-6"}}
+
+    config3 = config4 = None
+    if extras_on and shared and not args.no_configs:
+        config3 = config3_leg()
+        config4 = config4_leg()
+
+    # ---- what a reference user with a GPU runs today: the reference's ATen op sequence on this B200 (informational)
+    eager = None
+    if extras_on and rank == 0 and world == 1:
+        try:
+            from oracle import torch_port as TP
+            sd_dev = {k: v.to(dev) for k, v in make_state_dict(0, shared).items()}
+            Hb = H[:1024]
+            for _ in range(3):
+                TP.mc_head_torch(sd_dev, Hb, 100, 0.1, 0.1)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                TP.mc_head_torch(sd_dev, Hb, 100, 0.1, 0.1)
+            torch.cuda.synchronize(dev)
+            per = (time.perf_counter() - t0) / 20
+            eager = {"bags_per_s": 1.0 / per, "ms_per_bag": per * 1e3,
+                     "what": "oracle/torch_port.py (the reference's op sequence, fp32, torch eager, native CUDA dropout) on "
+                             "this GPU, one bag of N=1024, T=100 per call; informational, not the reference arm"}
+        except Exception as e:  # noqa: BLE001
+            eager = {"error": repr(e)}
 
     # ---- CPU baseline on this host (rank 0, N=1 only): bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         Ncpu, Tcpu = (1024, 100) if args.workload == "config2" else (lens[0], min(T, 25))
-        bps, times = cpu_head_bags_per_s(args.cpu_bags, Ncpu, Tcpu, shared, cores)
+        bps, times, head = cpu_head_bags_per_s(args.cpu_bags, Ncpu, Tcpu, shared, cores)
         cpu = {"value": bps * (Tcpu / (100 if args.workload == "config2" else T)), "unit": "bags/s", "cores": cores,
-               "kind": "port",
-               "sample": f"{args.cpu_bags} bag(s) of N={Ncpu}, T={Tcpu}: torch-CPU port of the reference head "
-                         f"(oracle/torch_port.py, native dropout), {cores} threads"}
+               "kind": head.kind,
+               "sample": f"{args.cpu_bags} bag(s) of N={Ncpu}, T={Tcpu}: {head.describe()}, {cores} threads"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "bags/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f16xf16->f32",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {len(all_lens) if strong else n_bags} bag(s)"
@@ -424,9 +644,10 @@ def run_ours(args):
                        "parallelism": "bags sharded over ranks, no collective" if args.workload != "config4"
                        else "MC samples sharded over ranks, one NCCL allreduce of Welford partials"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_f16_features": e2e_f16, "single_bag": single,
+            "separate": separate, "config3": config3, "config4": config4, "torch_cuda_eager": eager,
             "philox_rounds": args.philox_rounds, "philox7_mode": philox7,
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-            "clocks": clocks, "flops_per_step_per_gpu": flops_step,
+            "clocks": clocks, "flops_per_step_per_gpu": flops_step, "hbm_peak_gbs": hbm_peak,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -444,9 +665,11 @@ def main():
     ap.add_argument("--separate", action="store_true", help="shared_attention=False (config.yml default)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--e2e-chunk", type=int, default=32)
+    ap.add_argument("--e2e-streams", type=int, default=3)
     ap.add_argument("--cpu-bags", type=int, default=8)
     ap.add_argument("--philox-rounds", type=int, default=10, choices=[7, 10])
-    ap.add_argument("--no-extras", action="store_true", help="skip the Philox-7 and single-bag extras")
+    ap.add_argument("--no-extras", action="store_true", help="skip every extra leg (Philox-7, separate, single bag, configs 3/4)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config 3 / config 4 legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

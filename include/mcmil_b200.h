@@ -76,6 +76,16 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu_seqlens_host, const 
 int mcmil_plan_destroy(mcmil_plan_t* p);
 size_t mcmil_plan_workspace_bytes(const mcmil_plan_t* p);
 int mcmil_plan_total_rows(const mcmil_plan_t* p);
+/* Layout of the internal logit / score planes [T][C][plane_cols] (what mcmil_debug_proj_tc copies out): every bag
+ * starts at a multiple of 32 columns; mcmil_plan_bag_plane_col returns the first column of a bag (-1: bad index). */
+int mcmil_plan_plane_cols(const mcmil_plan_t* p);
+int mcmil_plan_bag_plane_col(const mcmil_plan_t* p, int bag);
+/* Kernels the reductions behind the projection take for this plan: 1 (a cluster of 8 CTAs per bag finishes softmax,
+ * pooling and the MC statistics in one launch: small batches whose per-bag slabs fit shared memory) or 2 (rows,
+ * then columns).  mcmil_set_reduce_path forces one of them process-wide (0 = automatic, 1 = two launches,
+ * 2 = one launch; tests and A/B measurements: both paths must agree). */
+int mcmil_plan_reduce_launches(const mcmil_plan_t* p);
+int mcmil_set_reduce_path(int path);
 
 /* ---- the hot path: model.py:280-316 + the MC statistics of infer.py:195,212-219 -------
  *   H            DEVICE fp32 [R][512] packed patch features (R = cu[n_bags])
@@ -86,7 +96,7 @@ int mcmil_plan_total_rows(const mcmil_plan_t* p);
  *                smallest Crush-resistant round count; ~25 % faster projection kernel)
  *   p_f, p_a     feature / logit dropout probabilities (model.py:141-142)
  *   inj_feat_keep_bits  DEVICE uint32 [T][R][16]   nullable; bit l%32 of word l/32: 1 = keep
- *   inj_attn_keep_bits  DEVICE uint32 [T][C][ceil(R/32)] nullable; bit r%32 of word r/32
+ *   inj_attn_keep_bits  DEVICE uint32 [T][C][ceil(R/32)] nullable; bit r%32 of word r/32 (r = packed row)
  *                (both or neither; when given they replace the Philox masks — this is how the
  *                 reference's own masks are injected for bit-exact comparison)
  *   impl         MCMIL_IMPL_*
@@ -133,7 +143,7 @@ int mcmil_export_masks(const mcmil_plan_t* plan, int t_offset, int bag_offset, u
 /* ---- debug (tests only; not a reference-facing entry point): feature packing + tcgen05
  * projection only; dumps every CTA's raw TMEM accumulators of its first (tile, sample):
  *   dbg DEVICE fp32 [grid][128 lanes][136] (128 accumulator columns + 8 score columns), and the
- *   dropped logits / classifier scores planes [T][C][Rp] (Rp = R rounded up to 32). */
+ *   dropped logits / classifier scores planes [T][C][mcmil_plan_plane_cols(plan)]. */
 int mcmil_debug_proj_tc(const mcmil_weights_t* w, const mcmil_plan_t* plan, const float* H, int t_offset,
                         int bag_offset, uint64_t seed, float p_f, float p_a,
                         const uint32_t* inj_feat_keep_bits, const uint32_t* inj_attn_keep_bits,
@@ -165,17 +175,17 @@ int mcmil_gather_tiles(const float* image, int channels, int H, int W, const int
  * T = 1 and p_f = p_a = 0 (threshold 0 keeps every element; Y[.][0][:] / A[0] are the outputs).
  * mcmil_aux_pairwise_loss replaces AuxiliaryLoss.pairwise_distance_loss (model.py:405-426) as the model
  * applies it per MC pass (model.py:318-326) or once (model.py:243-248):
- *   A     DEVICE fp32 [T][C][R] (mcmil_head_forward's A)
+ *   A     DEVICE fp32 [T][C][R] (mcmil_head_forward's A); T and R must be the plan's (checked)
  *   loss  DEVICE fp32 [n_bags][T]:  scale * (is_positive ? max(margin - d, 0) : d),
  *         d = || A[t][pos_head][bag rows] - A[t][neg_head][bag rows] + eps ||_2   (F.pairwise_distance)
  * The reference uses pos_head = 1, neg_head = 0, margin = 1.0, scale = 0.5 (model.py:149-151), eps = 1e-6. */
-int mcmil_aux_pairwise_loss(const mcmil_plan_t* plan, const float* A, int pos_head, int neg_head, int is_positive,
-                            float margin, float scale, float eps, float* loss, void* stream);
+int mcmil_aux_pairwise_loss(const mcmil_plan_t* plan, const float* A, int T, int R, int pos_head, int neg_head,
+                            int is_positive, float margin, float scale, float eps, float* loss, void* stream);
 
 /* ---- measurement hook (bench.py): brackets the tcgen05 projection launch(es) of the next
  * `max_calls` mcmil_head_forward calls with CUDA events on the launching stream;
  * mcmil_profile_end synchronises them and returns the summed device time and the number of
- * projection kernels covered.  Not thread-safe; off by default. */
+ * projection kernels covered.  One process-wide recorder (mutex-guarded); off by default. */
 int mcmil_profile_begin(int max_calls);
 int mcmil_profile_end(double* total_ms, int* kernels);
 

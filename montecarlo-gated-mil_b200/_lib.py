@@ -30,6 +30,10 @@ SIGNATURES = {
     "mcmil_plan_destroy": (_i, [_vp]),
     "mcmil_plan_workspace_bytes": (_sz, [_vp]),
     "mcmil_plan_total_rows": (_i, [_vp]),
+    "mcmil_plan_plane_cols": (_i, [_vp]),
+    "mcmil_plan_bag_plane_col": (_i, [_vp, _i]),
+    "mcmil_plan_reduce_launches": (_i, [_vp]),
+    "mcmil_set_reduce_path": (_i, [_i]),
     "mcmil_head_forward": (_i, [_vp, _vp, _vp, _i, _i, _u64, _i, _f, _f, _vp, _vp, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mcmil_head_forward_f16": (_i, [_vp, _vp, _vp, _i, _i, _u64, _i, _f, _f, _vp, _vp, _i,
@@ -42,7 +46,7 @@ SIGNATURES = {
     "mcmil_attnmap_stats": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mcmil_tile_nonzero_pct": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
     "mcmil_gather_tiles": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
-    "mcmil_aux_pairwise_loss": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp]),
+    "mcmil_aux_pairwise_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _vp, _vp]),
     "mcmil_profile_begin": (_i, [_i]),
     "mcmil_profile_end": (_i, [C.POINTER(_dbl), C.POINTER(_i)]),
 }

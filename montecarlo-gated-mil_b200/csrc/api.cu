@@ -5,6 +5,7 @@
 #include <new>
 #include <string>
 #include <cstdlib>
+#include <mutex>
 #include "internal.h"
 
 using namespace mcmil;
@@ -16,13 +17,16 @@ namespace {
 thread_local std::string g_err;
 thread_local int g_launches = 0;
 
-// optional CUDA-event bracketing of the projection kernel(s), for bench.py's roofline figure
+// optional CUDA-event bracketing of the projection kernel(s), for bench.py's roofline figure.  One process-wide
+// recorder guarded by a mutex (calls from several threads are serialised while it is on; off by default).
 struct Profile {
   bool on = false;
   std::vector<cudaEvent_t> ev;
   size_t used = 0;       // events recorded so far (pairs * 2)
   int kernels = 0;       // projection launches covered
 } g_prof;
+std::mutex g_prof_mu;
+int g_reduce_path = 0;   // mcmil_set_reduce_path (tests / A-B runs): 0 auto, 1 two launches, 2 one launch
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 int cuda_fail(cudaError_t e, const char* where) {
@@ -107,24 +111,37 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu, const int32_t* bag_
   p->n_bags = n_bags; p->T = T; p->C = num_classes;
   p->cu.assign(cu, cu + n_bags + 1);
   p->R = cu[n_bags];
-  p->Rp = (int)align_up((size_t)p->R, 32);
-  std::vector<int32_t> row2bag((size_t)p->R);
+  p->Rw = (p->R + 31) / 32;
+  std::vector<int32_t> row2bag((size_t)p->R), pcol((size_t)n_bags);
+  long long cols = 0;                        // every bag starts at a multiple of 32 plane columns (128 bytes)
   for (int b = 0; b < n_bags; ++b) {
     const int n = cu[b + 1] - cu[b];
     if (n > p->max_n) p->max_n = n;
+    pcol[(size_t)b] = (int32_t)cols;
     for (int n0 = 0; n0 < n; n0 += TILE_ROWS) {
       TileDesc td{}; td.bag = b; td.n0 = n0; td.row0 = cu[b] + n0; td.gbag = bag_ids ? bag_ids[b] : b;
       td.nrows = (n - n0 < TILE_ROWS) ? n - n0 : TILE_ROWS;
+      td.pcol0 = (int)cols + n0;
       p->tiles.push_back(td);
     }
     for (int r = cu[b]; r < cu[b + 1]; ++r) row2bag[(size_t)r] = b;
+    cols += (long long)align_up((size_t)n, 32);
   }
+  if (cols > 0x7fffffffLL || (long long)T * num_classes * cols > (1LL << 40)) {
+    delete p;
+    return fail(MCMIL_E_UNSUPPORTED, "mcmil_plan_create: batch too large for one call");
+  }
+  p->Rp = (int)cols;
   p->n_tiles = (int)p->tiles.size();
+  p->wsplit = welford_split(p->n_tiles, p->C, T);
+  p->fused_smem = fused_reduce_smem_bytes(T, p->C, p->max_n);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = dmalloc(&p->d_cu, (size_t)n_bags + 1);
   if (e == cudaSuccess) e = dmalloc(&p->d_tiles, (size_t)p->n_tiles);
   if (e == cudaSuccess) e = dmalloc(&p->d_row2bag, (size_t)p->R);
   if (e == cudaSuccess) e = dmalloc(&p->d_gbag, (size_t)n_bags);
+  if (e == cudaSuccess) e = dmalloc(&p->d_pcol, (size_t)n_bags);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_pcol, pcol.data(), sizeof(int32_t) * n_bags, cudaMemcpyHostToDevice, st);
   std::vector<int32_t> gbag((size_t)n_bags);
   for (int b = 0; b < n_bags; ++b) gbag[(size_t)b] = bag_ids ? bag_ids[b] : b;
   if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_gbag, gbag.data(), sizeof(int32_t) * n_bags, cudaMemcpyHostToDevice, st);
@@ -137,6 +154,8 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu, const int32_t* bag_
   p->off_logit = off;   off = align_up(off + (size_t)T * p->C * p->Rp * sizeof(float), 1024);
   p->off_score = off;   off = align_up(off + (size_t)T * p->C * p->Rp * sizeof(float), 1024);
   p->off_rowstat = off; off = align_up(off + (size_t)T * p->C * n_bags * sizeof(float2), 1024);
+  p->off_wpart = off;   off = align_up(off + (p->wsplit > 1 ? (size_t)p->wsplit * p->C * p->Rp * sizeof(float2) : 0), 1024);
+  p->off_wcount = off;  off = align_up(off + (size_t)p->n_tiles * p->C * sizeof(int), 1024);
   p->ws_bytes = off;
   *out = p;
   return 0;
@@ -144,12 +163,28 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu, const int32_t* bag_
 
 int mcmil_plan_destroy(mcmil_plan_t* p) {
   if (!p) return 0;
-  cudaFree(p->d_cu); cudaFree(p->d_tiles); cudaFree(p->d_row2bag); cudaFree(p->d_gbag);
+  cudaFree(p->d_cu); cudaFree(p->d_tiles); cudaFree(p->d_row2bag); cudaFree(p->d_gbag); cudaFree(p->d_pcol);
   delete p;
   return 0;
 }
 size_t mcmil_plan_workspace_bytes(const mcmil_plan_t* p) { return p ? p->ws_bytes : 0; }
 int mcmil_plan_total_rows(const mcmil_plan_t* p) { return p ? p->R : 0; }
+int mcmil_plan_plane_cols(const mcmil_plan_t* p) { return p ? p->Rp : 0; }
+int mcmil_plan_bag_plane_col(const mcmil_plan_t* p, int bag) {
+  if (!p || bag < 0 || bag >= p->n_bags) return -1;
+  int cols = 0;
+  for (int b = 0; b < bag; ++b) cols += (int)align_up((size_t)(p->cu[(size_t)b + 1] - p->cu[(size_t)b]), 32);
+  return cols;
+}
+int mcmil_plan_reduce_launches(const mcmil_plan_t* p) {
+  if (!p) return 0;
+  return (g_reduce_path == 2 || (g_reduce_path == 0 && p->fused_smem != 0 && p->n_bags * 8 <= 4 * 148)) ? 1 : 2;
+}
+int mcmil_set_reduce_path(int path) {
+  if (path < 0 || path > 2) return fail(MCMIL_E_BADARG, "mcmil_set_reduce_path: 0 (auto), 1 (two launches) or 2 (one launch)");
+  g_reduce_path = path;
+  return 0;
+}
 
 static int head_forward_impl(const mcmil_weights_t* w, const mcmil_plan_t* plan, const void* H, int h_f16,
                              int t_offset, int bag_offset, uint64_t seed, int philox_rounds, float p_f, float p_a,
@@ -175,14 +210,18 @@ static int head_forward_impl(const mcmil_weights_t* w, const mcmil_plan_t* plan,
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   float* logits = reinterpret_cast<float*>(ws + plan->off_logit);
   float* scores = reinterpret_cast<float*>(ws + plan->off_score);
-  float2* rowstat = reinterpret_cast<float2*>(ws + plan->off_rowstat);
   const MaskSpec m = make_mask_spec(t_offset, bag_offset, seed, philox_rounds, p_f, p_a, inj_feat, inj_attn);
   cudaError_t e;
   if (impl == MCMIL_IMPL_TCGEN05) {
-    const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
-    if (prof) cudaEventRecord(g_prof.ev[g_prof.used], st);
-    e = launch_proj_tc(*w, *plan, m, H, h_f16, logits, scores, nullptr, st, &g_launches);
-    if (prof) { cudaEventRecord(g_prof.ev[g_prof.used + 1], st); g_prof.used += 2; g_prof.kernels += w->S; }
+    if (g_prof.on) {                       // measurement mode: bracket the projection launch(es) with events
+      std::lock_guard<std::mutex> lock(g_prof_mu);
+      const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
+      if (prof) cudaEventRecord(g_prof.ev[g_prof.used], st);
+      e = launch_proj_tc(*w, *plan, m, H, h_f16, logits, scores, nullptr, st, &g_launches);
+      if (prof) { cudaEventRecord(g_prof.ev[g_prof.used + 1], st); g_prof.used += 2; g_prof.kernels += w->S; }
+    } else {
+      e = launch_proj_tc(*w, *plan, m, H, h_f16, logits, scores, nullptr, st, &g_launches);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "proj_tc");
   } else if (impl == MCMIL_IMPL_SIMT_FP32) {
     e = launch_proj_simt(*w, *plan, m, H, h_f16, logits, scores, st, &g_launches);
@@ -190,7 +229,7 @@ static int head_forward_impl(const mcmil_weights_t* w, const mcmil_plan_t* plan,
   } else {
     return fail(MCMIL_E_BADARG, "mcmil_head_forward: unknown impl");
   }
-  e = launch_reduce(*plan, logits, scores, rowstat, Y, A, prob_mean, prob_m2, attn_mean, attn_m2, st, &g_launches);
+  e = launch_reduce(*plan, logits, scores, ws, Y, A, prob_mean, prob_m2, attn_mean, attn_m2, g_reduce_path, st, &g_launches);
   if (e != cudaSuccess) return cuda_fail(e, "reduce");
   return 0;
 }
@@ -236,6 +275,7 @@ int mcmil_debug_proj_tc(const mcmil_weights_t* w, const mcmil_plan_t* plan, cons
 
 int mcmil_profile_begin(int max_calls) {
   if (max_calls < 1) return fail(MCMIL_E_BADARG, "mcmil_profile_begin: max_calls must be >= 1");
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
   g_prof.ev.assign((size_t)max_calls * 2, nullptr);
   for (auto& e : g_prof.ev) {
@@ -247,6 +287,7 @@ int mcmil_profile_begin(int max_calls) {
 }
 int mcmil_profile_end(double* total_ms, int* kernels) {
   if (!total_ms || !kernels) return fail(MCMIL_E_BADARG, "mcmil_profile_end: null pointer");
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   double total = 0.0;
   for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
     cudaError_t err = cudaEventSynchronize(g_prof.ev[i + 1]);
@@ -300,9 +341,11 @@ int mcmil_welford_unpack(const double* packed, int n, float* mean, float* m2, vo
   return e == cudaSuccess ? 0 : cuda_fail(e, "mcmil_welford_unpack");
 }
 
-int mcmil_aux_pairwise_loss(const mcmil_plan_t* plan, const float* A, int pos_head, int neg_head, int is_positive,
-                            float margin, float scale, float eps, float* loss, void* stream) {
+int mcmil_aux_pairwise_loss(const mcmil_plan_t* plan, const float* A, int T, int R, int pos_head, int neg_head,
+                            int is_positive, float margin, float scale, float eps, float* loss, void* stream) {
   if (!plan || !A || !loss) return fail(MCMIL_E_BADARG, "mcmil_aux_pairwise_loss: null argument");
+  if (T != plan->T || R != plan->R)
+    return fail(MCMIL_E_BADARG, "mcmil_aux_pairwise_loss: A is not the (T, C, R) attention of this plan");
   if (pos_head < 0 || pos_head >= plan->C || neg_head < 0 || neg_head >= plan->C)
     return fail(MCMIL_E_BADARG, "mcmil_aux_pairwise_loss: head index out of range");
   cudaError_t e = launch_aux_pairwise(*plan, A, pos_head, neg_head, is_positive, margin, scale, eps, loss, (cudaStream_t)stream);

@@ -30,7 +30,8 @@ struct TileDesc {
   int row0;     // first packed row (cu[bag] + n0)
   int nrows;    // valid rows in this tile, 1..128
   int gbag;     // global bag id keying the Philox masks (bag_ids[bag], or bag)
-  int pad_[3];
+  int pcol0;    // column of the tile's first patch in the logit / score planes (bag start padded to 32 columns)
+  int pad_[2];
 };
 
 // Epilogue constants of one (V,U) parameter set, passed in the kernel-parameter constant bank.

@@ -117,9 +117,8 @@ __global__ void export_feat_kernel(const int32_t* __restrict__ cu, const int32_t
   }
 }
 __global__ void export_attn_kernel(const int32_t* __restrict__ cu, const int32_t* __restrict__ row2bag,
-                                   const int32_t* __restrict__ gbag, int R, int Rp, int T, int C, MaskSpec m,
+                                   const int32_t* __restrict__ gbag, int R, int Rw, int T, int C, MaskSpec m,
                                    uint32_t* __restrict__ bits) {
-  const int Rw = Rp / 32;
   const size_t total = (size_t)T * C * Rw;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int wd = (int)(i % Rw);
@@ -141,7 +140,7 @@ __global__ void export_attn_kernel(const int32_t* __restrict__ cu, const int32_t
 cudaError_t launch_export_masks(const Plan& p, const MaskSpec& m, uint32_t* feat_bits, uint32_t* attn_bits,
                                 cudaStream_t st) {
   if (feat_bits) export_feat_kernel<<<1024, 256, 0, st>>>(p.d_cu, p.d_row2bag, p.d_gbag, p.R, p.T, m, feat_bits);
-  if (attn_bits) export_attn_kernel<<<256, 256, 0, st>>>(p.d_cu, p.d_row2bag, p.d_gbag, p.R, p.Rp, p.T, p.C, m, attn_bits);
+  if (attn_bits) export_attn_kernel<<<256, 256, 0, st>>>(p.d_cu, p.d_row2bag, p.d_gbag, p.R, p.Rw, p.T, p.C, m, attn_bits);
   return cudaGetLastError();
 }
 

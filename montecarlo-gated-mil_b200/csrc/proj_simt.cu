@@ -24,7 +24,7 @@ struct SimtParams {
   const TileDesc* tiles;
   float* logits; float* scores;
   const uint32_t* inj_feat; const uint32_t* inj_attn;
-  int T, C, R, Rp, n_out, head0, t_offset, bag_offset, rounds;
+  int T, C, R, Rp, Rw, n_out, head0, t_offset, bag_offset, rounds;
   uint32_t thr_f, thr_a;
   float sf, sa;
   PhiloxKey key;
@@ -159,9 +159,9 @@ proj_simt_kernel(const SimtParams P) {
           float logit = pv + __ldg(P.bw + head);
           bool keep;
           if (P.inj_attn == nullptr) keep = attn_keep_from(rnd, head, P.thr_a);
-          else keep = (P.inj_attn[((size_t)t * P.C + head) * (P.Rp >> 5) + (g >> 5)] >> (g & 31)) & 1u;
+          else keep = (P.inj_attn[((size_t)t * P.C + head) * P.Rw + (g >> 5)] >> (g & 31)) & 1u;
           logit = keep ? logit * P.sa : 0.f;
-          const size_t o = ((size_t)t * P.C + head) * P.Rp + g;
+          const size_t o = ((size_t)t * P.C + head) * P.Rp + td.pcol0 + trow;
           P.logits[o] = logit;
           P.scores[o] = sv;
         }
@@ -181,7 +181,7 @@ cudaError_t launch_proj_simt(const Weights& w, const Plan& p, const MaskSpec& m,
     P.tiles = p.d_tiles;
     P.logits = logits; P.scores = scores;
     P.inj_feat = m.inj_feat; P.inj_attn = m.inj_attn;
-    P.T = p.T; P.C = p.C; P.R = p.R; P.Rp = p.Rp;
+    P.T = p.T; P.C = p.C; P.R = p.R; P.Rp = p.Rp; P.Rw = p.Rw;
     P.n_out = w.shared ? w.C : 1;
     P.head0 = w.shared ? 0 : s;
     P.t_offset = m.t_offset; P.bag_offset = m.bag_offset;
@@ -196,7 +196,7 @@ cudaError_t launch_proj_simt(const Weights& w, const Plan& p, const MaskSpec& m,
       Q.logits = logits + (size_t)t0 * p.C * p.Rp;
       Q.scores = scores + (size_t)t0 * p.C * p.Rp;
       if (m.inj_feat) Q.inj_feat = m.inj_feat + (size_t)t0 * p.R * 16;
-      if (m.inj_attn) Q.inj_attn = m.inj_attn + (size_t)t0 * p.C * (p.Rp >> 5);
+      if (m.inj_attn) Q.inj_attn = m.inj_attn + (size_t)t0 * p.C * p.Rw;
       proj_simt_kernel<<<dim3(p.n_tiles * 2, tn), SM_THREADS, 0, st>>>(Q);
       if (launches) ++*launches;
     }

@@ -21,6 +21,7 @@
 //   sub-partition ~25 % of a sample time, and with two issuers the two producer warps sharing their
 //   sub-partitions were the laggards every K-slice barrier waited for (profiles/r1_experiments.md).
 #include <cstdio>
+#include <mutex>
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -75,9 +76,9 @@ enum : uint32_t {
   B_EMPTY = B_FULL + NMMA * NSLICE,   // [NMMA][8] per CTA: the MMAs reading the slot have retired     (count 1)
   B_TFULL = B_EMPTY + NMMA * NSLICE,  // [NBUF] per CTA: accumulator buffer complete                   (count 1)
   B_TEMPTY = B_TFULL + NBUF,          // [NMMA] leader only: both CTAs' epilogues drained the buffer   (count 8)
-  B_WLOC = B_TEMPTY + NMMA,           // per CTA: W bulk copies landed                                 (tx)
-  B_WREADY = B_WLOC + 1,              // leader only: both CTAs hold their W halves                    (count 2)
-  B_COUNT = B_WREADY + 1,
+  B_WLOC = B_TEMPTY + NMMA,           // [8] per CTA: the bulk copy of W K-slice s landed              (tx)
+  B_WREADY = B_WLOC + NSLICE,         // [8] leader only: both CTAs hold their halves of W K-slice s   (count 2)
+  B_COUNT = B_WREADY + NSLICE,
   TMEM_SLOT = 100                     // uint32 at SM_BAR + 8*100
 };
 static_assert(B_COUNT <= TMEM_SLOT && 8 * (TMEM_SLOT + 1) <= 1024, "barrier area");
@@ -98,9 +99,9 @@ struct ProjParams {
   float* logits;           // [T][C][Rp]
   float* scores;           // [T][C][Rp]
   const uint32_t* inj_feat;  // [T][R][16] or null
-  const uint32_t* inj_attn;  // [T][C][Rp/32] or null
+  const uint32_t* inj_attn;  // [T][C][Rw] or null (bit = packed row)
   float* dbg;              // optional raw accumulator dump of each pair's first (tile, t)
-  int n_tiles, T, C, R, Rp;
+  int n_tiles, T, C, R, Rp, Rw;   // Rp: plane columns (row stride of logits / scores); Rw: words per row of inj_attn
   int n_out;               // heads produced by this launch (shared: C, separate: 1)
   int head0;               // first head index written by this launch
   int t_offset, bag_offset;
@@ -257,8 +258,10 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     }
     for (int b = 0; b < NBUF; ++b) mbar_init(bar_addr(sbase, B_TFULL + b), 1);
     for (int b = 0; b < NMMA; ++b) mbar_init(bar_addr(sbase, B_TEMPTY + b), 8);
-    mbar_init(bar_addr(sbase, B_WLOC), 1);
-    mbar_init(bar_addr(sbase, B_WREADY), 2);
+    for (int s = 0; s < NSLICE; ++s) {
+      mbar_init(bar_addr(sbase, B_WLOC + s), 1);
+      mbar_init(bar_addr(sbase, B_WREADY + s), 2);
+    }
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
@@ -267,6 +270,18 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
   }
   tc_fence_before();
   __syncthreads();
+  // TMA loader: this CTA's W rows, once per kernel, one barrier per K-slice so the first MMAs can start as soon
+  // as slice 0 has landed (a single-bag call is ~11 samples per pair: the 136 KB load is not negligible there).
+  // Issued before the cluster barrier (only this CTA's own smem and barriers are involved) and before
+  // griddepcontrol.wait: INVARIANT — the W image is written once by mcmil_weights_create, which synchronises its
+  // stream before returning, so no kernel that precedes this one in any stream can still be writing it.
+  if (warp == LOAD_WARP && lane == 0) {
+    for (int s = 0; s < NSLICE; ++s) {
+      const uint32_t wloc = bar_addr(sbase, B_WLOC + s);
+      mbar_expect_tx(wloc, SLICE_BYTES_W);
+      bulk_g2s(sbase + SM_W + s * SLICE_BYTES_W, P.wmain + (size_t)(rank * NSLICE + s) * SLICE_BYTES_W, SLICE_BYTES_W, wloc);
+    }
+  }
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * TMEM_SLOT);
@@ -286,14 +301,13 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
 #ifndef MCMIL_NO_SETMAXNREG
     reg_dealloc<REGS_MMA>();
 #endif
-    // ------------------------------------------------------------ TMA loader: this CTA's W rows, once
+    // ------------------------------------------------------------ W slices landed -> tell the leader (after the
+    // cluster barrier: the leader's barriers are initialised)
     if (warp == LOAD_WARP && lane == 0) {
-      const uint32_t wloc = bar_addr(sbase, B_WLOC);
-      mbar_expect_tx(wloc, NSLICE * SLICE_BYTES_W);
-      for (int s = 0; s < NSLICE; ++s)
-        bulk_g2s(sbase + SM_W + s * SLICE_BYTES_W, P.wmain + (size_t)(rank * NSLICE + s) * SLICE_BYTES_W, SLICE_BYTES_W, wloc);
-      mbar_wait(wloc, 0);
-      mbar_arrive_cluster(mapa(bar_addr(sbase, B_WREADY), 0));
+      for (int s = 0; s < NSLICE; ++s) {
+        mbar_wait(bar_addr(sbase, B_WLOC + s), 0);
+        mbar_arrive_cluster(mapa(bar_addr(sbase, B_WREADY + s), 0));
+      }
     }
     __syncwarp();
     // ------------------------------------------------------------ MMA issuers (leader CTA)
@@ -313,8 +327,6 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       const uint32_t q = (uint32_t)(warp - MMA_WARP);          // this warp issues the samples tc = q (mod NMMA)
       uint32_t mbuf = q % NBUF;                                 // ... into TMEM accumulator buffer tc % NBUF
       uint32_t mslot = (q * TEAM_SLICES) % TEAM_SLOTS;          // ring slot (per team) of the sample's first slice
-      mbar_wait(bar_addr(sbase, B_WREADY), 0);
-      tc_fence_after();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t adesc0 = umma_desc_sw128(sbase + SM_RING);
       const uint64_t bdesc0 = umma_desc_sw128(sbase + SM_W);
@@ -334,6 +346,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
         bool full_ready = false;                                // early probe of the next slice's FULL barrier
 #pragma unroll 1
         for (int s = 0; s < NSLICE; ++s) {
+          if (j == 0) mbar_wait(bar_addr(sbase, B_WREADY + s), 0);     // this warp's first sample: W slice s of both CTAs
           if (!full_ready) WAIT_R(wait_a, bar_addr(sbase, B_FULL + q * NSLICE + s), j & 1, MCMIL_RELAXED_NS_FULL);
           tc_fence_after();
 #ifndef MCMIL_NO_EARLY_PROBE
@@ -614,7 +627,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
             const int head = P.head0 + c;
             bool keep;
             if constexpr (!INJECT) keep = attn_keep_from(rnd, head, P.thr_a);
-            else keep = (P.inj_attn[((size_t)t * P.C + head) * (P.Rp >> 5) + (g >> 5)] >> (g & 31)) & 1u;
+            else keep = (P.inj_attn[((size_t)t * P.C + head) * P.Rw + (g >> 5)] >> (g & 31)) & 1u;
             mult[c] = keep ? P.sa : 0.f;
           }
         }
@@ -634,7 +647,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
           for (int c = 0; c < NOUT; ++c) {
             const int head = P.head0 + c;
             const float logit = acc[c] + part[c] + P.epi.bw[c];
-            const size_t o = ((size_t)t * P.C + head) * P.Rp + g;
+            const size_t o = ((size_t)t * P.C + head) * P.Rp + td.pcol0 + trow;
             P.logits[o] = mult[c] != 0.f ? logit * mult[c] : 0.f;   // a dropped logit is 0, not -inf (model.py:291,305)
             P.scores[o] = (__uint_as_float(sc[c]) + __uint_as_float(sc[4 + c])) * P.sf;
           }
@@ -675,26 +688,33 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
        {proj_tc_kernel<1, MASK_INJECTED, false, 10>, proj_tc_kernel<2, MASK_INJECTED, false, 10>,
         proj_tc_kernel<3, MASK_INJECTED, false, 10>, proj_tc_kernel<4, MASK_INJECTED, false, 10>}}};
   static const KernelFn debug_kernel = proj_tc_kernel<2, MASK_PHILOX, true, 10>;   // raw-accumulator dump (tests only)
-  static bool attr_set = false;
-  if (!attr_set) {
-    for (int r = 0; r < 2; ++r)
-      for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 4; ++b) {
-          cudaError_t e = cudaFuncSetAttribute(kernels[r][a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
-          if (e != cudaSuccess) return e;
-        }
-    cudaError_t e = cudaFuncSetAttribute(debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
   if (dbg != nullptr && !(w.shared && w.C == 2 && m.inj_feat == nullptr && m.rounds == 10)) return cudaErrorInvalidValue;
+  // The dynamic shared memory opt-in is a PER-DEVICE function attribute and the SM count a per-device property:
+  // both are set / queried once per device ordinal, under a mutex (several host threads may drive several GPUs).
   int dev = 0;
-  cudaGetDevice(&dev);
-  static int sms_of[64] = {0};                       // SM count per device ordinal (queried once)
-  int sms = dev >= 0 && dev < 64 ? sms_of[dev] : 0;
-  if (sms == 0) {
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (dev >= 0 && dev < 64) sms_of[dev] = sms;
+  cudaError_t de = cudaGetDevice(&dev);
+  if (de != cudaSuccess) return de;
+  int sms = 0;
+  {
+    static std::mutex mu;
+    static int sms_of[64] = {0};                     // 0 = this device has not been set up yet
+    std::lock_guard<std::mutex> lock(mu);
+    const bool cached = dev >= 0 && dev < 64 && sms_of[dev] != 0;
+    if (!cached) {
+      for (int r = 0; r < 2; ++r)
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 4; ++b) {
+            cudaError_t e = cudaFuncSetAttribute(kernels[r][a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+            if (e != cudaSuccess) return e;
+          }
+      cudaError_t e = cudaFuncSetAttribute(debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+      if (e != cudaSuccess) return e;
+      e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (e != cudaSuccess) return e;
+      if (dev >= 0 && dev < 64) sms_of[dev] = sms;
+    } else {
+      sms = sms_of[dev];
+    }
   }
   const long long units = (long long)p.n_tiles * p.T;
   int n_pairs = sms / 2;
@@ -708,7 +728,7 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
     P.logits = logits; P.scores = scores;
     P.inj_feat = m.inj_feat; P.inj_attn = m.inj_attn;
     P.dbg = dbg;
-    P.n_tiles = p.n_tiles; P.T = p.T; P.C = p.C; P.R = p.R; P.Rp = p.Rp;
+    P.n_tiles = p.n_tiles; P.T = p.T; P.C = p.C; P.R = p.R; P.Rp = p.Rp; P.Rw = p.Rw;
     P.n_out = w.shared ? w.C : 1;
     P.head0 = w.shared ? 0 : s;
     P.t_offset = m.t_offset; P.bag_offset = m.bag_offset;

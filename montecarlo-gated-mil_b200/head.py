@@ -19,6 +19,7 @@ from . import _lib
 L_FEAT = 512
 D_HID = 128
 MAX_CLASSES = 4
+FP16_MAX = 65504.0
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -119,6 +120,24 @@ _plan_cache: dict = {}
 _workspaces: dict = {}
 
 
+def _check_cu(what: str, cu_seqlens, R: int) -> np.ndarray:
+    """Bag boundaries of a packed batch: host ints, start at 0, end at R, strictly increasing."""
+    cu = np.array([0, R], np.int64) if cu_seqlens is None else np.asarray(cu_seqlens, dtype=np.int64)
+    if cu.ndim != 1 or len(cu) < 2 or cu[0] != 0 or cu[-1] != R or np.any(np.diff(cu) <= 0):
+        raise ValueError(f"{what}: cu_seqlens must start at 0, end at the number of packed rows ({R}) and be "
+                         "strictly increasing")
+    return cu.astype(np.int32)
+
+
+def set_reduce_path(path: str = "auto") -> None:
+    """Tests / A-B measurements: force the reductions behind the projection onto the one-launch ("fused") or the
+    two-launch ("split") path; "auto" (default) picks per plan.  Both paths compute the same outputs."""
+    code = {"auto": 0, "split": 1, "fused": 2}.get(path)
+    if code is None:
+        raise ValueError("set_reduce_path: auto / split / fused")
+    _lib.check(_lib.load().mcmil_set_reduce_path(code), "mcmil_set_reduce_path")
+
+
 def _get_plan(cu: np.ndarray, T: int, C_: int, device, bag_ids=None) -> _Plan:
     ids_key = None if bag_ids is None else np.asarray(bag_ids, np.int32).tobytes()
     key = (cu.tobytes(), ids_key, int(T), int(C_), str(device))
@@ -178,7 +197,7 @@ def mc_head(weights: HeadWeights, H: torch.Tensor, T: int, seed: int = 0,
             keep_f_bits: Optional[torch.Tensor] = None, keep_a_bits: Optional[torch.Tensor] = None,
             return_attention: bool = False, t_offset: int = 0, bag_offset: int = 0,
             bag_ids: Optional[Sequence[int]] = None, impl: str = "tcgen05",
-            philox_rounds: int = 10) -> MCHeadResult:
+            philox_rounds: int = 10, validate: bool = False) -> MCHeadResult:
     """Run T MC-dropout passes of the GA-MIL head on packed features.
 
     H            (R, 512) fp32 (or fp16) CUDA, contiguous: one bag (cu_seqlens=None) or a packed batch
@@ -187,6 +206,9 @@ def mc_head(weights: HeadWeights, H: torch.Tensor, T: int, seed: int = 0,
     keep_f_bits  optional injected feature keep-mask, uint32/int32 (T, R, 16) CUDA
     keep_a_bits  optional injected logit keep-mask, (T, C, ceil(R/32)) CUDA   (both or neither)
     philox_rounds  10 (Philox4x32-10, default) or 7 (Philox4x32-7, ~25 % faster)
+    validate     True: check (one reduction over H + a host sync) that the features are finite and inside the fp16
+                 range the tensor-core path rounds them to (|h| <= 65504; ResNet avg-pool features are O(1-10)), and
+                 raise ValueError otherwise.  Off by default: without it such features give inf / NaN outputs.
     """
     lib = _lib.load()
     if not isinstance(H, torch.Tensor) or H.device.type != "cuda":
@@ -200,10 +222,12 @@ def mc_head(weights: HeadWeights, H: torch.Tensor, T: int, seed: int = 0,
     if impl not in _lib.IMPLS:
         raise ValueError(f"mc_head: impl must be one of {sorted(_lib.IMPLS)}")
     R = H.shape[0]
-    cu = np.array([0, R], np.int32) if cu_seqlens is None else np.asarray(cu_seqlens, dtype=np.int64)
-    if cu.ndim != 1 or len(cu) < 2 or cu[0] != 0 or cu[-1] != R or np.any(np.diff(cu) <= 0):
-        raise ValueError("mc_head: cu_seqlens must start at 0, end at H.shape[0] and be strictly increasing")
-    cu = cu.astype(np.int32)
+    cu = _check_cu("mc_head", cu_seqlens, R)
+    if validate and R > 0:
+        amax = float(H.abs().max())
+        if not np.isfinite(amax) or (impl == "tcgen05" and amax > FP16_MAX):
+            raise ValueError(f"mc_head: features must be finite and within the fp16 range (|h| <= {FP16_MAX:g}) of the "
+                             f"tensor-core path; max |h| = {amax:g}.  Use impl='simt_fp32' or rescale the features.")
     if T < 1:
         raise ValueError("mc_head: T must be >= 1")
     dev = H.device
@@ -258,9 +282,13 @@ class MCHeadRunner:
                  philox_rounds: int = 10, impl: str = "tcgen05"):
         self.lib = _lib.load()
         self.w, self.dev, self.T, self.R = weights, weights.device, int(T), int(n_rows)
-        cu = np.array([0, n_rows], np.int32) if cu_seqlens is None else np.asarray(cu_seqlens, dtype=np.int32)
-        if cu[0] != 0 or cu[-1] != n_rows or np.any(np.diff(cu) <= 0) or T < 1:
-            raise ValueError("MCHeadRunner: bad cu_seqlens / T")
+        if impl not in _lib.IMPLS:
+            raise ValueError(f"MCHeadRunner: impl must be one of {sorted(_lib.IMPLS)}")
+        if T < 1 or n_rows < 1:
+            raise ValueError("MCHeadRunner: T and n_rows must be >= 1")
+        if philox_rounds not in (7, 10) or not (0.0 <= p_f <= 1.0 and 0.0 <= p_a <= 1.0):
+            raise ValueError("MCHeadRunner: philox_rounds must be 10 or 7 and the dropout probabilities in [0, 1]")
+        cu = _check_cu("MCHeadRunner", cu_seqlens, int(n_rows))
         C_ = weights.num_classes
         self.plan = _get_plan(cu, T, C_, self.dev)
         nb = self.plan.n_bags
@@ -287,11 +315,13 @@ class MCHeadRunner:
         return self.result
 
 
-def head_forward_eval(weights: HeadWeights, H: torch.Tensor, cu_seqlens: Optional[Sequence[int]] = None):
+def head_forward_eval(weights: HeadWeights, H: torch.Tensor, cu_seqlens: Optional[Sequence[int]] = None,
+                      impl: str = "tcgen05", validate: bool = False):
     """Deterministic (eval-mode) forward of the head, /root/reference/model.py:216-240 with the dropout
     modules inactive: one pass of the same fused kernels with every mask element kept.
     Returns (Y (n_bags, C) logits, A (C, R) attention)."""
-    res = mc_head(weights, H, 1, seed=0, p_f=0.0, p_a=0.0, cu_seqlens=cu_seqlens, return_attention=True)
+    res = mc_head(weights, H, 1, seed=0, p_f=0.0, p_a=0.0, cu_seqlens=cu_seqlens, return_attention=True, impl=impl,
+                  validate=validate)
     return res.Y[:, 0, :], res.A[0]
 
 
@@ -309,12 +339,13 @@ def aux_pairwise_loss(A: torch.Tensor, is_positive: bool, cu_seqlens: Optional[S
     T, C_, R = A.shape
     if not (0 <= pos_head < C_ and 0 <= neg_head < C_):
         raise ValueError("aux_pairwise_loss: needs the two heads it compares (the reference uses heads 1 and 0)")
-    cu = np.array([0, R], np.int32) if cu_seqlens is None else np.asarray(cu_seqlens, dtype=np.int32)
+    cu = _check_cu("aux_pairwise_loss", cu_seqlens, R)
     dev = A.device
     plan = _get_plan(cu, T, C_, dev)
     with torch.cuda.device(dev):
         out = torch.empty((plan.n_bags, T), dtype=torch.float32, device=dev)
-        _lib.check(lib.mcmil_aux_pairwise_loss(plan._h, _ptr(A), int(pos_head), int(neg_head), int(bool(is_positive)),
+        _lib.check(lib.mcmil_aux_pairwise_loss(plan._h, _ptr(A), int(T), int(R), int(pos_head), int(neg_head),
+                                               int(bool(is_positive)),
                                                float(margin), float(scale), float(eps), _ptr(out), _stream_ptr(dev)),
                    "mcmil_aux_pairwise_loss")
     return out
@@ -327,7 +358,12 @@ def export_masks(T: int, R_or_cu, num_classes: int, seed: int, p_f: float, p_a: 
     dev = torch.device(device)
     if dev.index is None:
         dev = torch.device("cuda", torch.cuda.current_device())
-    cu = np.array([0, int(R_or_cu)], np.int32) if np.isscalar(R_or_cu) else np.asarray(R_or_cu, np.int32)
+    if np.isscalar(R_or_cu):
+        cu = _check_cu("export_masks", None, int(R_or_cu))
+    else:
+        cu = _check_cu("export_masks", R_or_cu, int(np.asarray(R_or_cu)[-1]))
+    if T < 1 or not 1 <= num_classes <= MAX_CLASSES or philox_rounds not in (7, 10):
+        raise ValueError("export_masks: T >= 1, num_classes in [1,4], philox_rounds 10 or 7")
     plan = _get_plan(cu, T, num_classes, dev)
     R = plan.R
     with torch.cuda.device(dev):
@@ -346,9 +382,9 @@ def debug_proj_tc(weights: HeadWeights, H: torch.Tensor, T: int, seed: int, p_f:
     lib = _lib.load()
     dev = H.device
     R = H.shape[0]
-    cu = np.array([0, R], np.int32) if cu_seqlens is None else np.asarray(cu_seqlens, np.int32)
+    cu = _check_cu("debug_proj_tc", cu_seqlens, R)
     plan = _get_plan(cu, T, weights.num_classes, dev)
-    Rp = (R + 31) // 32 * 32
+    Rp = int(lib.mcmil_plan_plane_cols(plan._h))
     with torch.cuda.device(dev):
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         dbg = torch.zeros((sms, 128, 136), dtype=torch.float32, device=dev)

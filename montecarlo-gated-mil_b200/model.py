@@ -21,6 +21,26 @@ class Identity(nn.Module):
         return x
 
 
+class AuxiliaryLoss(nn.Module):
+    """Same surface as the reference's AuxiliaryLoss (/root/reference/model.py:405-438): `loss_type` 'pairwise'
+    (L2 distance between the positive and the negative head's attention, hinged at `margin` for positive bags) or
+    'cosine'; callers read `.scale` (model.py:246,322).  Plain torch: it is the training-time regulariser; the
+    inference paths compute the pairwise form on the device with mcmil_aux_pairwise_loss."""
+
+    def __init__(self, loss_type="pairwise", margin=1.0, scale=1.0):
+        super().__init__()
+        self.loss_type, self.margin, self.scale = loss_type, margin, scale
+
+    def forward(self, pos_attention, neg_attention, is_positive):
+        if self.loss_type == "pairwise":
+            d = F.pairwise_distance(pos_attention, neg_attention, p=2)
+            return torch.mean((self.margin - d).clamp(min=0)) if is_positive else torch.mean(d)
+        if self.loss_type == "cosine":
+            cs = F.cosine_similarity(pos_attention, neg_attention, dim=1)
+            return torch.mean(cs) if is_positive else torch.mean(1 - cs)
+        raise ValueError(f"Unknown loss type: {self.loss_type}")
+
+
 def _make_backbone(backbone: str, pretrained: bool):
     import torchvision.models as tvm
     ctor = {"r18": tvm.resnet18, "r34": tvm.resnet34, "r50": tvm.resnet50}
@@ -40,6 +60,13 @@ class _ExtractorRunner:
 
     def __init__(self):
         self.graphs = {}          # (shape, device) -> (graph, static_in, static_out)
+        self.fingerprint = None   # storage of the extractor's parameters / buffers the graphs were captured against
+
+    @staticmethod
+    def _fingerprint(module: nn.Module):
+        """A captured graph bakes in the addresses of the parameters and buffers: any move / cast / re-assignment
+        of them (model.cpu().cuda(), .half(), load_state_dict(assign=True)) must drop the graphs."""
+        return tuple((t.data_ptr(), t.dtype, tuple(t.shape)) for t in list(module.parameters()) + list(module.buffers()))
 
     def run(self, module: nn.Module, x: torch.Tensor, mode: str) -> torch.Tensor:
         if mode == "eager":
@@ -48,12 +75,15 @@ class _ExtractorRunner:
             raise ValueError(f"extractor_mode must be eager / channels_last / graph, got {mode!r}")
         if x.device.type != "cuda":
             raise RuntimeError("extractor_mode channels_last / graph need CUDA tensors")
-        if next(module.parameters()).dim() and not getattr(module, "_mcmil_cl", False):
-            module.to(memory_format=torch.channels_last)
-            module._mcmil_cl = True
+        if any(p.dim() == 4 and not p.is_contiguous(memory_format=torch.channels_last) for p in module.parameters()):
+            module.to(memory_format=torch.channels_last)      # (re-done after any move that reset the layout)
         x = x.contiguous(memory_format=torch.channels_last)
         if mode == "channels_last":
             return module(x)
+        fp = self._fingerprint(module)
+        if fp != self.fingerprint:
+            self.graphs.clear()
+            self.fingerprint = fp
         key = (tuple(x.shape), str(x.device))
         ent = self.graphs.get(key)
         if ent is None:
@@ -82,6 +112,7 @@ class MultiHeadGatedAttentionMIL(nn.Module):
         super().__init__()
         if L != 512 or D != 128:
             raise NotImplementedError("the B200 head is built for L=512, D=128 (the reference defaults)")
+        self.auxiliary_loss = AuxiliaryLoss(loss_type="pairwise", margin=1.0, scale=.5)      # model.py:149-151
         self.fold_idx = None
         self.neptune_run = neptune_run
         self.L, self.D = L, D
@@ -102,12 +133,27 @@ class MultiHeadGatedAttentionMIL(nn.Module):
         self._packed = None          # (HeadWeights, version key)
         self.mc_seed = 0             # Philox key of the next mc_inference call (auto-incremented)
         self.last_result: MCHeadResult | None = None
-        self.fused_eval = True       # eval-mode forward() through the fused head (forward_eval_fused)
+        # Eval-mode, no-grad, CUDA forward() goes through the fused head (forward_eval_fused): features and weights
+        # are rounded to fp16 for the tensor cores and tanh is the hardware approximation, so logits differ from the
+        # fp32 torch graph by up to ~2e-3 absolute (attention ~1e-4 relative).  Set False to keep the plain torch
+        # graph, or `fused_eval_impl = "simt_fp32"` for the fused path in full fp32.
+        self.fused_eval = True
+        self.fused_eval_impl = "tcgen05"
+        self.validate_features = False   # True: raise if the extractor's features are not finite or exceed fp16 range
         self.extractor_mode = "eager"  # "channels_last" / "graph": how torch runs the extractor for mc_inference
         self._extractor_runner = _ExtractorRunner()
 
     # ------------------------------------------------------------------ forward (model.py:211-253)
-    AUX_MARGIN, AUX_SCALE = 1.0, 0.5          # AuxiliaryLoss(loss_type='pairwise', margin=1.0, scale=.5), model.py:149-151
+    @property
+    def AUX_MARGIN(self):
+        return float(self.auxiliary_loss.margin)
+
+    @property
+    def AUX_SCALE(self):
+        return float(self.auxiliary_loss.scale)
+
+    def _aux_fused_ok(self):
+        return self.auxiliary_loss.loss_type == "pairwise"
 
     def forward(self, x, targets=None):
         """Training keeps the plain-torch graph (autograd).  Deterministic inference — eval mode, grad
@@ -130,10 +176,8 @@ class MultiHeadGatedAttentionMIL(nn.Module):
         A_all = torch.cat(A_all, dim=1)
         Y = torch.cat([self.classifiers[i](M[:, i, :]) for i in range(self.num_classes)], dim=-1)
         aux = None
-        if targets is not None:
-            d = F.pairwise_distance(A_all[:, 1, :], A_all[:, 0, :])
-            # model.py:405-426 (pairwise, margin 1.0, scale 0.5): push the heads apart on positives
-            aux = 0.5 * (torch.clamp(1.0 - d, min=0).mean() if targets.item() == 1 else d.mean())
+        if targets is not None:                     # model.py:243-248
+            aux = self.auxiliary_loss.scale * self.auxiliary_loss(A_all[:, 1, :], A_all[:, 0, :], targets.item() == 1)
         return Y, A_all, aux
 
     def forward_eval_fused(self, x, targets=None):
@@ -146,14 +190,19 @@ class MultiHeadGatedAttentionMIL(nn.Module):
         with torch.no_grad():
             H = self.feature_extractor(x.view(bs * n, *x.shape[2:])).view(bs * n, -1).float().contiguous()
             cu = [i * n for i in range(bs + 1)]
-            Y, A = head_forward_eval(self._head_weights(x.device), H, cu)          # (bs, C), (C, bs*n)
+            Y, A = head_forward_eval(self._head_weights(x.device), H, cu, impl=self.fused_eval_impl,
+                                     validate=self.validate_features)             # (bs, C), (C, bs*n)
             A_all = A.view(self.num_classes, bs, n).permute(1, 0, 2).contiguous()   # (bs, C, n)
             aux = None
             if targets is not None:
                 if self.num_classes < 2:
                     raise RuntimeError("the auxiliary loss compares heads 1 and 0 (model.py:246-247)")
-                aux = aux_pairwise_loss(A.view(1, self.num_classes, bs * n), targets.item() == 1, cu,
-                                        margin=self.AUX_MARGIN, scale=self.AUX_SCALE).mean()   # torch.mean over bs
+                if self._aux_fused_ok():
+                    aux = aux_pairwise_loss(A.view(1, self.num_classes, bs * n), targets.item() == 1, cu,
+                                            margin=self.AUX_MARGIN, scale=self.AUX_SCALE).mean()   # torch.mean over bs
+                else:                                   # 'cosine' (model.py:428-438): tiny, torch on the device
+                    aux = self.auxiliary_loss.scale * self.auxiliary_loss(A_all[:, 1, :], A_all[:, 0, :],
+                                                                          targets.item() == 1)
         return Y, A_all, aux
 
     # ------------------------------------------------------------------ the B200 hot path
@@ -195,7 +244,7 @@ class MultiHeadGatedAttentionMIL(nn.Module):
             res = mc_head(self._head_weights(device), H, int(N), seed=seed,
                           p_f=float(self.feature_dropout.p), p_a=float(self.attention_dropouts[0].p),
                           keep_f_bits=keep_f_bits, keep_a_bits=keep_a_bits,
-                          return_attention=return_attention, impl=impl)
+                          return_attention=return_attention, impl=impl, validate=self.validate_features)
         self.last_result = res
         return res
 
@@ -213,9 +262,20 @@ class MultiHeadGatedAttentionMIL(nn.Module):
             return Y, A
         losses = None
         if targets is not None and self.num_classes >= 2:           # model.py:318-326: one loss per MC pass
-            per_pass = aux_pairwise_loss(res.A, targets.item() == 1, margin=self.AUX_MARGIN, scale=self.AUX_SCALE)[0]
-            losses = list(per_pass.unbind(0))
+            if self._aux_fused_ok():
+                per_pass = aux_pairwise_loss(res.A, targets.item() == 1, margin=self.AUX_MARGIN, scale=self.AUX_SCALE)[0]
+                losses = list(per_pass.unbind(0))
+            else:
+                losses = [self.auxiliary_loss.scale * self.auxiliary_loss(res.A[i, 1:2], res.A[i, 0:1], targets.item() == 1)
+                          for i in range(res.A.shape[0])]
         return Y, A, losses
+
+    def mc_inference_serial(self, input_tensor, N=30, device="cuda"):
+        """The reference's second MC entry point (/root/reference/model.py:330-401): N bag-sized passes in a Python
+        loop (~20 s per bag on the reference's CPU path).  Same distribution of (predictions (N,bs,C),
+        attention_weights (N,bs,C,n)) as `mc_inference`; here it is the same fused batched call (the reference's
+        two paths also draw different samples for the same seed: they consume the RNG in different orders)."""
+        return self.mc_inference(input_tensor, N=N, device=device)
 
 
 def deactivate_batchnorm(m):

@@ -59,6 +59,7 @@ class ImagePatcher:
         self.empty_thresh = empty_thresh
         self.tiles = None
         self._tiles_dev = None
+        self._tiles_src = None        # the `self.tiles` array the device copy was made from
 
     # ---- grid (image_patcher.py:16-41) -------------------------------------------------------
     def _start_points(self, size, split_size):
@@ -83,9 +84,21 @@ class ImagePatcher:
         return tiles
 
     def _tiles_on(self, dev):
-        if self._tiles_dev is None or self._tiles_dev.device != dev:
-            self._tiles_dev = torch.from_numpy(self.tiles.astype(np.int32)).to(dev).contiguous()
+        # `self.tiles` may be assigned directly (the reference's dataset sets patcher.tiles per image,
+        # dataset.py:60-66): the device copy follows the identity of the host array
+        if self._tiles_dev is None or self._tiles_dev.device != dev or self._tiles_src is not self.tiles:
+            self._tiles_dev = torch.from_numpy(np.asarray(self.tiles).astype(np.int32)).to(dev).contiguous()
+            self._tiles_src = self.tiles
         return self._tiles_dev
+
+    def _check_image(self, h, w):
+        """The reference slices `image[:, y:y+p, x:x+p]` and fails on a shape mismatch (image_patcher.py:52); the
+        kernels index raw memory, so the grid must fit the image."""
+        if self.tiles is None or len(self.tiles) == 0:
+            raise RuntimeError("ImagePatcher: call get_tiles(h, w) first")
+        t = np.asarray(self.tiles)
+        if t[:, 0].min() < 0 or t[:, 1].min() < 0 or t[:, 0].max() + self.patch_size > h or t[:, 1].max() + self.patch_size > w:
+            raise ValueError(f"ImagePatcher: the tile grid does not fit a {h}x{w} image (grid built for another size?)")
 
     # ---- bag selection (image_patcher.py:43-59, 115-131) -----------------------------------------
     def tile_nonzero_pct(self, image: torch.Tensor) -> torch.Tensor:
@@ -94,6 +107,7 @@ class ImagePatcher:
             raise RuntimeError("ImagePatcher (B200): the image must be a CUDA tensor")
         image = image.float().contiguous()
         c, h, w = image.shape
+        self._check_image(h, w)
         tiles = self._tiles_on(image.device)
         pct = torch.empty(tiles.shape[0], dtype=torch.float32, device=image.device)
         with torch.cuda.device(image.device):
@@ -101,10 +115,17 @@ class ImagePatcher:
                                                   _stream(image.device)), "mcmil_tile_nonzero_pct")
         return pct
 
-    def convert_img_to_bag(self, image: torch.Tensor, shuffle: bool = False, generator=None):
+    def convert_img_to_bag(self, image: torch.Tensor, shuffle: bool = False, generator=None, random_state=None):
         """image (c,H,W) CUDA -> (instances (n,c,p,p), instances_idx (n,), instances_cords (n,2)).
-        The reference returns the selected tiles in a random order (sklearn.utils.shuffle,
-        image_patcher.py:131); here the order is descending non-empty fraction unless shuffle=True."""
+
+        Order of the returned tiles: descending non-empty fraction (ties by tile index) by default.  The reference
+        returns them shuffled (sklearn.utils.shuffle, image_patcher.py:131): `shuffle=True` permutes on the device
+        (`generator`), `shuffle="reference"` applies sklearn's own permutation (`random_state`, host side) like the
+        reference.  Tie order: the reference sorts with numpy's unstable argsort (image_patcher.py:56), so WHICH of
+        several equally non-empty tiles survive a `bag_size` cut is unspecified there; here ties go to the lower
+        tile index (stable sort).  With bag_size = -1 the selected set is identical.
+        One host read (the number of non-empty tiles sizes the bag tensor) — the reference's output shape is data
+        dependent too."""
         lib = _lib.load()
         image = image.float().contiguous()
         c, h, w = image.shape
@@ -118,7 +139,11 @@ class ImagePatcher:
         else:
             raise ValueError("Invalid bag size")
         sel = order[:n_sel]
-        if shuffle and n_sel > 1:
+        if shuffle == "reference" and n_sel > 1:
+            from sklearn.utils import shuffle as sk_shuffle
+            perm = sk_shuffle(np.arange(n_sel), random_state=random_state)
+            sel = sel[torch.from_numpy(np.asarray(perm)).to(sel.device)]
+        elif shuffle and n_sel > 1:
             sel = sel[torch.randperm(n_sel, generator=generator, device=sel.device)]
         sel32 = sel.to(torch.int32).contiguous()
         bag = torch.empty((n_sel, c, self.patch_size, self.patch_size), dtype=torch.float32, device=image.device)

@@ -140,3 +140,55 @@ def test_allreduce_welford_gloo_world2():
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, 101, 333, out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def test_auxiliary_loss_surface():
+    """The drop-in exposes the reference's `auxiliary_loss` attribute (model.py:149-151) with both loss types
+    (model.py:415-438); values against the closed forms."""
+    import mcmil_b200 as mm
+    from mcmil_b200.model import AuxiliaryLoss
+    from oracle import gamil_oracle as G
+    m = mm.MultiHeadGatedAttentionMIL(pretrained=False)
+    assert (m.auxiliary_loss.loss_type, m.auxiliary_loss.margin, m.auxiliary_loss.scale) == ("pairwise", 1.0, 0.5)
+    assert not [k for k in m.state_dict() if "auxiliary" in k]          # no parameters: the state_dict schema is unchanged
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.softmax(torch.randn(1, 50, generator=g), -1), torch.softmax(torch.randn(1, 50, generator=g), -1)
+    for pos in (True, False):
+        want = G.aux_pairwise_loss(a.numpy()[0], b.numpy()[0], pos, margin=1.0, scale=1.0)
+        assert abs(float(AuxiliaryLoss("pairwise", 1.0, 1.0)(a, b, pos)) - float(want)) < 1e-6
+    cs = float((a * b).sum() / (a.norm() * b.norm()))
+    assert abs(float(AuxiliaryLoss("cosine")(a, b, True)) - cs) < 1e-6
+    assert abs(float(AuxiliaryLoss("cosine")(a, b, False)) - (1 - cs)) < 1e-6
+    with pytest.raises(ValueError):
+        AuxiliaryLoss("nope")(a, b, True)
+
+
+def test_bench_reference_arm_uses_the_reference_module_when_present():
+    """bench.py --impl reference: the unmodified reference module (baseline/_ref or /root/reference) when it is there,
+    else the port; with the same torch seed both give the same (Y, A) — the port stands in faithfully."""
+    import bench
+    from oracle import torch_port as TP
+    head = bench.CpuHead(True, 2)
+    assert head.kind in ("reference", "port")
+    H = torch.relu(torch.randn(32, 512, generator=torch.Generator().manual_seed(3)))
+    torch.manual_seed(11)
+    Y, A = head.run(H, 4)
+    assert Y.shape == (4, 1, 2) and A.shape == (4, 1, 2, 32)
+    if head.kind == "reference":
+        torch.manual_seed(11)
+        Yp, Ap = TP.mc_head_torch(head.sd, H, 4, 0.1, 0.1)
+        assert torch.equal(Y, Yp) and torch.equal(A, Ap)
+
+
+def test_patcher_grid_must_fit_the_image_and_follows_tiles_assignment():
+    import mcmil_b200 as mm
+    pt = mm.ImagePatcher(patch_size=32, overlap=0.5)
+    pt.get_tiles(100, 80)
+    pt._check_image(100, 80)
+    with pytest.raises(ValueError):
+        pt._check_image(90, 80)              # grid built for a larger image
+    with pytest.raises(RuntimeError):
+        mm.ImagePatcher()._check_image(10, 10)
+    src = pt._tiles_src
+    pt.tiles = pt.tiles.copy()               # the reference's dataset assigns patcher.tiles directly
+    assert pt._tiles_src is src and pt._tiles_src is not pt.tiles   # stale until the next use refreshes it
