@@ -34,12 +34,13 @@ struct TileDesc {
   int pad_[2];
 };
 
-// Epilogue constants of one (V,U) parameter set, passed in the kernel-parameter constant bank.
-struct EpiConst {
-  float bv[D];          // attention_V bias
-  float hbu[D];         // 0.5 * attention_U bias       (sigmoid(x) = 0.5*tanh(0.5x)+0.5)
-  float hw[MAXC][D];    // 0.5 * attention_weights[c].weight
-  float bw[MAXC];       // attention_weights[c].bias
+// Epilogue constants of one (V,U) parameter set, passed in the kernel-parameter constant bank.  Laid out per PAIR
+// of hidden units (d, d+1), d even: the packed fp32x2 FMAs of the epilogue take their constant operand as one aligned
+// 64-bit uniform register pair, so one 16-byte constant load feeds two FFMA2 with no register shuffling.
+struct alignas(16) EpiConst {
+  float4 vb[D / 2];            // (bv[d], bv[d+1], 0.5*bu[d], 0.5*bu[d+1])       (sigmoid(x) = 0.5*tanh(0.5x)+0.5)
+  float2 hw[D / 2][MAXC];      // 0.5 * attention_weights[c].weight[d], [d+1]
+  float bw[MAXC];              // attention_weights[c].bias
 };
 
 __host__ __device__ inline int drop_threshold(float p) {

@@ -82,15 +82,15 @@ cudaError_t launch_pack_weights(Weights& w, const float* attV_w, const float* at
   w.epi.assign(S, EpiConst{});
   for (int s = 0; s < S; ++s) {
     EpiConst& ec = w.epi[s];
-    for (int d = 0; d < D; ++d) {
-      ec.bv[d] = bv[s * D + d];
-      ec.hbu[d] = 0.5f * bu[s * D + d];
-    }
+    for (int d = 0; d < D; d += 2)
+      ec.vb[d / 2] = make_float4(bv[s * D + d], bv[s * D + d + 1], 0.5f * bu[s * D + d], 0.5f * bu[s * D + d + 1]);
     for (int c = 0; c < MAXC; ++c) {
       // shared: slot c <-> head c; separate: slot 0 <-> head s
       const int head = w.shared ? c : (c == 0 ? s : -1);
-      for (int d = 0; d < D; ++d) ec.hw[c][d] = (head >= 0 && head < C) ? 0.5f * ww[head * D + d] : 0.f;
-      ec.bw[c] = (head >= 0 && head < C) ? bw[head] : 0.f;
+      const bool on = head >= 0 && head < C;
+      for (int d = 0; d < D; d += 2)
+        ec.hw[d / 2][c] = on ? make_float2(0.5f * ww[head * D + d], 0.5f * ww[head * D + d + 1]) : make_float2(0.f, 0.f);
+      ec.bw[c] = on ? bw[head] : 0.f;
     }
   }
   return cudaSuccess;

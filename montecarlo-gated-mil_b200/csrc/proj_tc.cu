@@ -209,19 +209,25 @@ __device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tbuf
 #endif
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
-        const int d = 64 * part + 32 * HALF + 16 * j + i;
-        const uint64_t xv = fma2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sf2,
-                                 pack2(P.epi.bv[d], P.epi.bv[d + 1]));
-        const uint64_t xu = fma2(pack2(__uint_as_float(u[i]), __uint_as_float(u[i + 1])), hsf2,
-                                 pack2(P.epi.hbu[d], P.epi.hbu[d + 1]));
+        const int pr = (64 * part + 32 * HALF + 16 * j + i) >> 1;         // pair of hidden units (d, d+1)
+        // one 16-byte constant load: (bv[d], bv[d+1]) | (0.5 bu[d], 0.5 bu[d+1]) as two aligned 64-bit operands
+        const ulonglong2 cb = *reinterpret_cast<const ulonglong2*>(&P.epi.vb[pr]);
+        const uint64_t xv = fma2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sf2, cb.x);
+        const uint64_t xu = fma2(pack2(__uint_as_float(u[i]), __uint_as_float(u[i + 1])), hsf2, cb.y);
         float xv0, xv1, xu0, xu1;
         unpack2(xv, xv0, xv1);
         unpack2(xu, xu0, xu1);
         const uint64_t av = pack2(tanh_approx(xv0), tanh_approx(xv1));
         const uint64_t au = pack2(tanh_approx(xu0), tanh_approx(xu1));
         const uint64_t g2 = fma2(av, au, av);          // 2 * tanh(.) * sigmoid(.)
-#pragma unroll
-        for (int c = 0; c < NOUT; ++c) acc2[c] = fma2(g2, pack2(P.epi.hw[c][d], P.epi.hw[c][d + 1]), acc2[c]);
+        const ulonglong2 h01 = *reinterpret_cast<const ulonglong2*>(&P.epi.hw[pr][0]);
+        acc2[0] = fma2(g2, h01.x, acc2[0]);
+        if constexpr (NOUT > 1) acc2[1] = fma2(g2, h01.y, acc2[1]);
+        if constexpr (NOUT > 2) {
+          const ulonglong2 h23 = *reinterpret_cast<const ulonglong2*>(&P.epi.hw[pr][2]);
+          acc2[2] = fma2(g2, h23.x, acc2[2]);
+          if constexpr (NOUT > 3) acc2[3] = fma2(g2, h23.y, acc2[3]);
+        }
       }
     }
   }
@@ -429,13 +435,16 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       return (int32_t)tp >= 0 && tcv != 0u;
     };
     TRACE_DECL
+    // the tile table belongs to the plan (written once, before any launch): the first descriptor is fetched before
+    // griddepcontrol.wait, off the critical path of a single-bag call
+    const TileDesc td_first = P.tiles[(int)(u_begin / P.T)];
     grid_dep_wait();
     for (long long u = u_begin; u < u_end;) {
       const int ti = (int)(u / P.T);
       const int t_begin = (int)(u - (long long)ti * P.T);
       const long long u_next = (long long)(ti + 1) * P.T;
       const int t_end = (int)((u_next < u_end ? u_next : u_end) - (long long)ti * P.T);
-      const TileDesc td = P.tiles[ti];
+      const TileDesc td = u == u_begin ? td_first : P.tiles[ti];
       const uint32_t bag = (uint32_t)(P.bag_offset + td.gbag);
       // this thread's 16 chunks (4 slices of its team x 4 row slots) of the fp16 feature tile: registers
       uint4 hreg[TEAM_SLICES][4];
@@ -569,6 +578,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     float* xch = reinterpret_cast<float*>(smem + SM_XCH);
     uint32_t tc = 0, buf = 0, buf_phase = 0;      // accumulator buffer tc % NBUF and the parity of its use count
     TRACE_DECL
+    const TileDesc td_first = P.tiles[(int)(u_begin / P.T)];     // plan-owned table: safe before griddepcontrol.wait
     grid_dep_wait();
 #ifdef MCMIL_EXP_PRODUCER_ONLY
     for (long long u = u_end; u < u_end;) {
@@ -579,7 +589,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       const int t_begin = (int)(u - (long long)ti * P.T);
       const long long u_next = (long long)(ti + 1) * P.T;
       const int t_end = (int)((u_next < u_end ? u_next : u_end) - (long long)ti * P.T);
-      const TileDesc td = P.tiles[ti];
+      const TileDesc td = u == u_begin ? td_first : P.tiles[ti];
       const int trow = (int)rank * HALF_ROWS + r;
       const bool valid = trow < td.nrows;
       const int g = td.row0 + trow;

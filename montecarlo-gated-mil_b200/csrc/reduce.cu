@@ -60,39 +60,54 @@ __device__ __forceinline__ void wf_merge(float& n_a, float& mu, float& q, float 
   q += qb + dlt * dlt * __fdividef(n_a * n_b, n_ab);
   n_a = n_ab;
 }
+// softmax_c of one sample's logits (C <= MAXC, register-only: no runtime-indexed arrays)
+__device__ __forceinline__ void softmax_classes(const float* y, int C, float (&p)[MAXC]) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) { p[c] = c < C ? y[c] : -INFINITY; mx = fmaxf(mx, p[c]); }
+  float z = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) { p[c] = fast_exp(p[c] - mx); z += p[c]; }      // exp(-inf) = 0 for c >= C
+  const float iz = 1.0f / z;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) p[c] *= iz;
+}
 // mean / M2 over t of softmax_c(y[t][:]) by one warp (two passes: the values are tiny); y: T x C, any address space
 __device__ __forceinline__ void prob_stats_warp(const float* y, int T, int C, int lane, float* prob_mean, float* prob_m2) {
   float s[MAXC] = {0.f, 0.f, 0.f, 0.f};
   for (int t = lane; t < T; t += 32) {
-    float mx = -INFINITY, p[MAXC], z = 0.f;
-    for (int c = 0; c < C; ++c) mx = fmaxf(mx, y[t * C + c]);
-    for (int c = 0; c < C; ++c) { p[c] = __expf(y[t * C + c] - mx); z += p[c]; }
-    for (int c = 0; c < C; ++c) s[c] += p[c] / z;
+    float p[MAXC];
+    softmax_classes(y + t * C, C, p);
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) s[c] += p[c];
   }
   float mean[MAXC];
-  for (int c = 0; c < C; ++c) mean[c] = warp_sum(s[c]) / (float)T;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) mean[c] = warp_sum(s[c]) / (float)T;
   float q[MAXC] = {0.f, 0.f, 0.f, 0.f};
   for (int t = lane; t < T; t += 32) {
-    float mx = -INFINITY, p[MAXC], z = 0.f;
-    for (int c = 0; c < C; ++c) mx = fmaxf(mx, y[t * C + c]);
-    for (int c = 0; c < C; ++c) { p[c] = __expf(y[t * C + c] - mx); z += p[c]; }
-    for (int c = 0; c < C; ++c) { const float dlt = p[c] / z - mean[c]; q[c] = fmaf(dlt, dlt, q[c]); }
+    float p[MAXC];
+    softmax_classes(y + t * C, C, p);
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) { const float dlt = p[c] - mean[c]; q[c] = fmaf(dlt, dlt, q[c]); }
   }
-  for (int c = 0; c < C; ++c) {
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
     const float qq = warp_sum(q[c]);
-    if (lane == 0) { prob_mean[c] = mean[c]; if (prob_m2) prob_m2[c] = qq; }
+    if (lane == 0 && c < C) { prob_mean[c] = mean[c]; if (prob_m2) prob_m2[c] = qq; }
   }
 }
 
 // ================================================================================== generic path, launch 1: rows
 constexpr int ROW_THREADS = 256;
 
-// Rows of up to 128 * V4 patches: one WARP per (bag, t, c) row, eight rows per CTA.  Both planes of the row are
-// loaded into registers up front (2 * V4 independent 512-byte warp loads in flight), max and exp / sum run on the
-// registers (each plane is read from DRAM exactly once), shuffle reductions only.  Block 0 also clears the arrival
-// counters of the column kernel.
-template <int V4>
-__global__ void __launch_bounds__(ROW_THREADS)
+// One WARP per (bag, t, c) row, eight rows per CTA, any row length: the row is walked in chunks of 1024 patches
+// (8 float4 per lane and plane, all 16 loads of a chunk issued before the first use); max and exp / sum of a chunk run
+// on the registers, chunks are merged with the running (max, sum) on the fly, so each plane is read from DRAM exactly
+// once.  Two CTAs per SM (98 registers) keep the loads of other warps in flight while one warp reduces.  Block 0 also
+// clears the arrival counters of the column kernel.
+constexpr int ROWW_V4 = 8;
+__global__ void __launch_bounds__(ROW_THREADS, 2)
 softmax_rows_warp_kernel(const float* __restrict__ logits, const float* __restrict__ scores,
                          const int32_t* __restrict__ cu, const int32_t* __restrict__ pcol, int n_bags, int T, int C,
                          int Rp, float2* __restrict__ rowstat, float* __restrict__ Y, int* __restrict__ wcount,
@@ -110,36 +125,44 @@ softmax_rows_warp_kernel(const float* __restrict__ logits, const float* __restri
   const size_t off = ((size_t)t * C + c) * Rp + pcol[b];
   const float4* lg = reinterpret_cast<const float4*>(logits + off);
   const float4* sc = reinterpret_cast<const float4*>(scores + off);
-  float4 v[V4], w[V4];
+  float M = -INFINITY, Z = 0.f, Yv = 0.f;                     // running row statistics (warp-uniform)
+  for (int base = 0; base < n; base += 128 * ROWW_V4) {
+    float4 v[ROWW_V4], w[ROWW_V4];
 #pragma unroll
-  for (int k = 0; k < V4; ++k) {
-    const int i4 = lane + 32 * k;
-    if (4 * i4 < n) { v[k] = __ldg(lg + i4); w[k] = __ldg(sc + i4); }
-    else { v[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); w[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
-  }
-  float m = -INFINITY;
+    for (int k = 0; k < ROWW_V4; ++k) {
+      const int i4 = base / 4 + lane + 32 * k;
+      if (4 * i4 < n) { v[k] = __ldg(lg + i4); w[k] = __ldg(sc + i4); }
+      else { v[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); w[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    }
+    float m = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < V4; ++k) {
-    const int col = 4 * (lane + 32 * k);                     // the bag's last float4 may reach into the plane padding
-    if (col + 1 >= n) { v[k].y = -INFINITY; w[k].y = 0.f; }
-    if (col + 2 >= n) { v[k].z = -INFINITY; w[k].z = 0.f; }
-    if (col + 3 >= n) { v[k].w = -INFINITY; w[k].w = 0.f; }
-    m = fmaxf(fmaxf(m, fmaxf(v[k].x, v[k].y)), fmaxf(v[k].z, v[k].w));
-  }
-  m = warp_max(m);
-  float z = 0.f, y = 0.f;
+    for (int k = 0; k < ROWW_V4; ++k) {
+      const int col = base + 4 * (lane + 32 * k);             // the bag's last float4 may reach into the plane padding
+      if (col + 1 >= n) { v[k].y = -INFINITY; w[k].y = 0.f; }
+      if (col + 2 >= n) { v[k].z = -INFINITY; w[k].z = 0.f; }
+      if (col + 3 >= n) { v[k].w = -INFINITY; w[k].w = 0.f; }
+      m = fmaxf(fmaxf(m, fmaxf(v[k].x, v[k].y)), fmaxf(v[k].z, v[k].w));
+    }
+    m = warp_max(m);
+    float z = 0.f, y = 0.f;
 #pragma unroll
-  for (int k = 0; k < V4; ++k) {
-    const float e0 = fast_exp(v[k].x - m), e1 = fast_exp(v[k].y - m);      // exp(-inf) = 0 for the padding
-    const float e2 = fast_exp(v[k].z - m), e3 = fast_exp(v[k].w - m);
-    z += (e0 + e1) + (e2 + e3);
-    y = fmaf(e0, w[k].x, y); y = fmaf(e1, w[k].y, y); y = fmaf(e2, w[k].z, y); y = fmaf(e3, w[k].w, y);
+    for (int k = 0; k < ROWW_V4; ++k) {
+      const float e0 = fast_exp(v[k].x - m), e1 = fast_exp(v[k].y - m);      // exp(-inf) = 0 for the padding
+      const float e2 = fast_exp(v[k].z - m), e3 = fast_exp(v[k].w - m);
+      z += (e0 + e1) + (e2 + e3);
+      y = fmaf(e0, w[k].x, y); y = fmaf(e1, w[k].y, y); y = fmaf(e2, w[k].z, y); y = fmaf(e3, w[k].w, y);
+    }
+    z = warp_sum(z); y = warp_sum(y);
+    const float Mn = fmaxf(M, m);
+    const float fa = fast_exp(M - Mn), fb = fast_exp(m - Mn);               // exp(-inf) = 0 on the first chunk
+    Z = fmaf(Z, fa, z * fb);
+    Yv = fmaf(Yv, fa, y * fb);
+    M = Mn;
   }
-  z = warp_sum(z); y = warp_sum(y);
   if (lane == 0) {
-    const float inv = 1.0f / z;
-    rowstat[((size_t)c * n_bags + b) * T + t] = make_float2(m, inv);   // [C][n_bags][T]: a row's samples are contiguous
-    Y[((size_t)b * T + t) * C + c] = y * inv;
+    const float inv = 1.0f / Z;
+    rowstat[((size_t)c * n_bags + b) * T + t] = make_float2(M, inv);   // [C][n_bags][T]: a row's samples are contiguous
+    Y[((size_t)b * T + t) * C + c] = Yv * inv;
   }
 }
 
@@ -220,20 +243,36 @@ softmax_rows_cta_kernel(const float* __restrict__ logits, const float* __restric
 
 // ================================================================================== generic path, launch 2: columns
 constexpr int COL_LANES = 32;
-constexpr int COL_VEC = 4;        // patches per lane: one 16-byte access per sample
+constexpr int COL_VEC = 4;        // patches per lane: one 16-byte load per sample
 constexpr int COL_COLS = COL_LANES * COL_VEC;   // = TILE_ROWS: one CTA works on one 128-patch tile of one bag
 constexpr int COL_TGROUPS = 8;    // the CTA's samples are strided over 8 warps, then merged in a fixed order
 constexpr int COL_THREADS = COL_LANES * COL_TGROUPS;
-constexpr int COL_CHUNK_T = 64;   // samples staged in shared memory at a time (32 KB)
+constexpr int COL_UNROLL = 4;     // samples a warp has in flight (independent 512-byte loads)
 constexpr int COL_MAX_SPLIT = 16;
 static_assert(COL_COLS == TILE_ROWS, "one column CTA per projection tile");
 
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t r, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
 // grid (n_tiles + bag_blocks, C, wsplit).
 // blockIdx.x < n_tiles: CTA = (tile of <= 128 patches of one bag, head c, sample group z): samples
-//   [T z / wsplit, T (z+1) / wsplit).  The CTA's slab of the logit plane (512 contiguous bytes per sample) is
-//   staged through shared memory with cp.async in chunks of 64 samples (8 independent 16-byte copies per thread
-//   in flight, no registers held); warp g runs Welford over the chunk's samples g, g+8, ..., each lane on 4
-//   adjacent patches, and the 8 partial (count, mean, M2) per patch are merged with Chan's formula in warp order.
+//   [T z / wsplit, T (z+1) / wsplit).  Warp g takes the group's samples g, g+8, ...: every lane reads 4 adjacent patches
+//   of a sample with one 16-byte load (512 contiguous bytes per warp and sample), four samples in flight per warp, no
+//   shared-memory staging; A = exp(l - max) / sum and the Welford update run as packed fp32x2 operations (two patches
+//   per instruction).  The 8 partial (count, mean, M2) per patch are merged with Chan's formula in warp order.
 //   wsplit > 1 (few tiles, many samples: one large bag): every CTA writes its partial to the workspace and the
 //   LAST CTA of the (tile, head) to arrive (one integer atomic per CTA) merges the groups in the order 0..wsplit-1,
 //   so the result does not depend on the arrival order.  Optionally stores A.
@@ -255,83 +294,109 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
     prob_stats_warp(Y + (size_t)b * T * C, T, C, lane, prob_mean + b * C, prob_m2 ? prob_m2 + b * C : nullptr);
     return;
   }
-  __shared__ __align__(16) float s_lg[COL_CHUNK_T][COL_COLS];
   __shared__ float s_mean[COL_TGROUPS][COL_COLS], s_m2[COL_TGROUPS][COL_COLS];
   __shared__ int s_cnt[COL_TGROUPS];
   __shared__ int s_last;
-  const TileDesc td = tiles[blockIdx.x];
+  const int nrows = tiles[blockIdx.x].nrows, pcol0 = tiles[blockIdx.x].pcol0, row0 = tiles[blockIdx.x].row0;
+  const int bag = tiles[blockIdx.x].bag;
   const int c = blockIdx.y, z = blockIdx.z;
   const int t_lo = (int)((long long)T * z / wsplit), t_hi = (int)((long long)T * (z + 1) / wsplit);
-  const int segs = (td.nrows + 3) >> 2;                      // 16-byte pieces per sample (the last one may reach
-                                                             // into the bag's plane padding: copied, never used)
-  const float* plane = logits + (size_t)c * Rp + td.pcol0;
-  const float2* rs_row = rowstat + ((size_t)c * n_bags + td.bag) * T;
-  float mean[COL_VEC] = {0.f, 0.f, 0.f, 0.f}, m2[COL_VEC] = {0.f, 0.f, 0.f, 0.f};
+  // (the last 16-byte load of the tile may reach into the bag's plane padding: loaded, its results never stored)
+  const float* plane = logits + (size_t)c * Rp + pcol0 + lane * COL_VEC;
+  const size_t tstride = (size_t)C * Rp;
+  const float2* rs_row = rowstat + ((size_t)c * n_bags + bag) * T;
+  uint64_t mean01 = 0ull, mean23 = 0ull, q01 = 0ull, q23 = 0ull;
   int cnt = 0;
-  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(&s_lg[0][0]);
-  const bool active = lane * COL_VEC < td.nrows;
-  for (int t0 = t_lo; t0 < t_hi; t0 += COL_CHUNK_T) {
-    const int nt = min(COL_CHUNK_T, t_hi - t0);
-    for (int p = threadIdx.x; p < nt * (COL_COLS / 4); p += COL_THREADS) {
-      const int row = p / (COL_COLS / 4), seg = p % (COL_COLS / 4);
-      if (seg < segs)
-        cp_async16(s_base + (uint32_t)(row * COL_COLS + seg * 4) * 4u, plane + (size_t)(t0 + row) * C * Rp + seg * 4);
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    if (active) {
-#pragma unroll 4
-      for (int r = grp; r < nt; r += COL_TGROUPS) {
-        const float4 l4 = *reinterpret_cast<const float4*>(&s_lg[r][lane * COL_VEC]);
-        const float lg[COL_VEC] = {l4.x, l4.y, l4.z, l4.w};
-        const float2 rs = __ldg(rs_row + t0 + r);
-        ++cnt;
-        const float inv_cnt = fast_rcp((float)cnt);
+  constexpr float LOG2E = 1.4426950408889634f;
+  if (lane * COL_VEC < nrows) {
+    for (int t = t_lo + grp; t < t_hi; t += COL_TGROUPS * COL_UNROLL) {
+      float4 l4[COL_UNROLL];
+      float2 rs[COL_UNROLL];
 #pragma unroll
-        for (int k = 0; k < COL_VEC; ++k) {
-          const float a = fast_exp(lg[k] - rs.x) * rs.y;
+      for (int u = 0; u < COL_UNROLL; ++u) {
+        const int tu = t + u * COL_TGROUPS;
+        if (tu < t_hi) {
+          l4[u] = __ldg(reinterpret_cast<const float4*>(plane + (size_t)tu * tstride));
+          rs[u] = __ldg(rs_row + tu);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < COL_UNROLL; ++u) {
+        const int tu = t + u * COL_TGROUPS;
+        if (tu < t_hi) {
+          // a = 2^(l log2e - max log2e) / sum, two patches per instruction
+          const float nm = -rs[u].x * LOG2E;
+          const uint64_t k2 = f2_pack(LOG2E, LOG2E), nm2 = f2_pack(nm, nm), inv2 = f2_pack(rs[u].y, rs[u].y);
+          float x0, x1, x2, x3;
+          f2_unpack(f2_fma(f2_pack(l4[u].x, l4[u].y), k2, nm2), x0, x1);
+          f2_unpack(f2_fma(f2_pack(l4[u].z, l4[u].w), k2, nm2), x2, x3);
+          float e0, e1, e2, e3;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(x2));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(x3));
+          const uint64_t a01 = f2_mul(f2_pack(e0, e1), inv2), a23 = f2_mul(f2_pack(e2, e3), inv2);
           if constexpr (HAS_A) {
-            if (lane * COL_VEC + k < td.nrows) A[((size_t)(t0 + r) * C + c) * R + td.row0 + lane * COL_VEC + k] = a;
+            float a0, a1, a2, a3;
+            f2_unpack(a01, a0, a1);
+            f2_unpack(a23, a2, a3);
+            float* dst = A + ((size_t)tu * C + c) * R + row0 + lane * COL_VEC;
+            const int left = nrows - lane * COL_VEC;
+            dst[0] = a0;
+            if (left > 1) dst[1] = a1;
+            if (left > 2) dst[2] = a2;
+            if (left > 3) dst[3] = a3;
           }
-          wf_push(mean[k], m2[k], a, inv_cnt);
+          ++cnt;
+          const float ic = fast_rcp((float)cnt);
+          const uint64_t ic2 = f2_pack(ic, ic);
+          const uint64_t d01 = f2_sub(a01, mean01), d23 = f2_sub(a23, mean23);
+          mean01 = f2_fma(d01, ic2, mean01);
+          mean23 = f2_fma(d23, ic2, mean23);
+          q01 = f2_fma(d01, f2_sub(a01, mean01), q01);
+          q23 = f2_fma(d23, f2_sub(a23, mean23), q23);
         }
       }
     }
-    __syncthreads();                                         // the next chunk overwrites s_lg
   }
-#pragma unroll
-  for (int k = 0; k < COL_VEC; ++k) { s_mean[grp][lane * COL_VEC + k] = mean[k]; s_m2[grp][lane * COL_VEC + k] = m2[k]; }
-  if (lane == 0) s_cnt[grp] = cnt;
+  {
+    float m0, m1, m2_, m3, v0, v1, v2, v3;
+    f2_unpack(mean01, m0, m1); f2_unpack(mean23, m2_, m3);
+    f2_unpack(q01, v0, v1); f2_unpack(q23, v2, v3);
+    *reinterpret_cast<float4*>(&s_mean[grp][lane * COL_VEC]) = make_float4(m0, m1, m2_, m3);
+    *reinterpret_cast<float4*>(&s_m2[grp][lane * COL_VEC]) = make_float4(v0, v1, v2, v3);
+    if (lane == 0) s_cnt[grp] = cnt;
+  }
   __syncthreads();
   const int col = threadIdx.x;
   float mu = 0.f, q = 0.f, n_a = 0.f;
-  if (col < td.nrows) {
+  if (col < nrows) {
 #pragma unroll
     for (int k = 0; k < COL_TGROUPS; ++k) wf_merge(n_a, mu, q, (float)s_cnt[k], s_mean[k][col], s_m2[k][col]);
   }
   if (wsplit == 1) {
-    if (col < td.nrows) {
-      if (attn_mean) attn_mean[(size_t)c * R + td.row0 + col] = mu;
-      if (attn_m2) attn_m2[(size_t)c * R + td.row0 + col] = q;
+    if (col < nrows) {
+      if (attn_mean) attn_mean[(size_t)c * R + row0 + col] = mu;
+      if (attn_m2) attn_m2[(size_t)c * R + row0 + col] = q;
     }
     return;
   }
-  if (col < td.nrows) wpart[((size_t)z * C + c) * Rp + td.pcol0 + col] = make_float2(mu, q);
+  if (col < nrows) wpart[((size_t)z * C + c) * Rp + pcol0 + col] = make_float2(mu, q);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(&wcount[blockIdx.x * C + c], 1) == wsplit - 1;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (col < td.nrows) {
+  if (col < nrows) {
     mu = 0.f; q = 0.f; n_a = 0.f;
     for (int k = 0; k < wsplit; ++k) {
-      const float2 pk = __ldcg(&wpart[((size_t)k * C + c) * Rp + td.pcol0 + col]);
+      const float2 pk = __ldcg(&wpart[((size_t)k * C + c) * Rp + pcol0 + col]);
       const int nk = (int)((long long)T * (k + 1) / wsplit) - (int)((long long)T * k / wsplit);
       wf_merge(n_a, mu, q, (float)nk, pk.x, pk.y);
     }
-    if (attn_mean) attn_mean[(size_t)c * R + td.row0 + col] = mu;
-    if (attn_m2) attn_m2[(size_t)c * R + td.row0 + col] = q;
+    if (attn_mean) attn_mean[(size_t)c * R + row0 + col] = mu;
+    if (attn_m2) attn_m2[(size_t)c * R + row0 + col] = q;
   }
 }
 
@@ -356,7 +421,7 @@ int welford_split(int n_tiles, int C, int T) {
 constexpr int FR_CL = 8;
 constexpr int FR_THREADS = 512;
 constexpr int FR_TG = 2;          // sample groups of phase 3 (t = g, g + 2, ...)
-constexpr int FR_RPI = 4;         // rows a warp works on at a time in phase 1 (independent shuffle chains)
+constexpr int FR_RPI = 8;         // rows a warp works on at a time in phase 1 (independent shuffle chains)
 constexpr size_t FR_SMEM_MAX = 220 * 1024;
 
 __host__ __device__ inline int fr_slab_cols(int n) { return ((n + FR_CL - 1) / FR_CL + 3) & ~3; }
@@ -497,20 +562,36 @@ fused_bag_reduce_kernel(const float* __restrict__ logits, const float* __restric
     __syncthreads();
   }
 
-  // ---- phase 3: attention values of the slab, Welford over the samples
+  // ---- phase 3: attention values of the slab, Welford over the samples (4 samples in flight per thread: the
+  // loads, exponentials and reciprocal counts are independent, only the two-instruction Welford chain is serial)
   const int items = ncols * C;
   for (int it = threadIdx.x; it < items * FR_TG; it += FR_THREADS) {
     const int col = it % ncols, rest = it / ncols;
     const int c = rest % C, tg = rest / C;
     float mean = 0.f, m2 = 0.f;
     int cnt = 0;
-    for (int t = tg; t < T; t += FR_TG) {
-      const int row = t * C + c;
-      const float2 st = stat[row];
-      const float a = fast_exp(slabL[(size_t)row * Wp + col] - st.x) * st.y;
-      if constexpr (HAS_A) A[(size_t)row * R + r0 + col0 + col] = a;
-      ++cnt;
-      wf_push(mean, m2, a, fast_rcp((float)cnt));
+    const float* lp = slabL + (size_t)c * Wp + col;
+    const size_t rstride = (size_t)C * Wp;
+    for (int t = tg; t < T; t += 4 * FR_TG) {
+      float a[4], ic[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tu = t + u * FR_TG;
+        if (tu < T) {
+          const float2 st = stat[tu * C + c];
+          a[u] = fast_exp(lp[(size_t)tu * rstride] - st.x) * st.y;
+          ic[u] = fast_rcp((float)(cnt + u + 1));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tu = t + u * FR_TG;
+        if (tu < T) {
+          if constexpr (HAS_A) A[(size_t)(tu * C + c) * R + r0 + col0 + col] = a[u];
+          wf_push(mean, m2, a[u], ic[u]);
+        }
+      }
+      cnt += 4;
     }
     p3[((size_t)tg * C + c) * Wp + col] = make_float2(mean, m2);
   }
@@ -527,8 +608,56 @@ fused_bag_reduce_kernel(const float* __restrict__ logits, const float* __restric
     if (attn_mean) attn_mean[o] = mu;
     if (attn_m2) attn_m2[o] = q;
   }
-  if (rank == 0 && warp == 0 && prob_mean != nullptr)
-    prob_stats_warp(yv, T, C, lane, prob_mean + b * C, prob_m2 ? prob_m2 + b * C : nullptr);
+  // ---- statistics of softmax_c(Y) over the samples: rank 0, one thread per sample, two block reductions
+  // (mean first, then the squared deviations: the two-pass form of the column kernel's prob_stats_warp)
+  if (rank == 0 && prob_mean != nullptr) {
+    __shared__ float s_red[2][FR_THREADS / 32][MAXC];
+    float s[MAXC] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = threadIdx.x; t < T; t += FR_THREADS) {
+      float pt[MAXC];
+      softmax_classes(yv + t * C, C, pt);
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) s[c] += pt[c];
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) s[c] = warp_sum(s[c]);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) s_red[0][warp][c] = s[c];
+    }
+    __syncthreads();
+    float mean[MAXC], q[MAXC] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < FR_THREADS / 32; ++w) tot += s_red[0][w][c];
+      mean[c] = tot / (float)T;
+    }
+    for (int t = threadIdx.x; t < T; t += FR_THREADS) {
+      float pt[MAXC];
+      softmax_classes(yv + t * C, C, pt);
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) { const float dlt = pt[c] - mean[c]; q[c] = fmaf(dlt, dlt, q[c]); }
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) q[c] = warp_sum(q[c]);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) s_red[1][warp][c] = q[c];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < C) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < FR_THREADS / 32; ++w) tot += s_red[1][w][threadIdx.x];
+      float mc = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) mc = c == (int)threadIdx.x ? mean[c] : mc;
+      prob_mean[b * C + threadIdx.x] = mc;
+      if (prob_m2) prob_m2[b * C + threadIdx.x] = tot;
+    }
+  }
   fr_cluster_sync();                                          // no CTA leaves while a peer may still read its part[]
 }
 
@@ -584,16 +713,11 @@ cudaError_t launch_reduce(const Plan& p, const float* logits, const float* score
     const long long rows = (long long)p.n_bags * p.T * p.C;
     const unsigned warp_grid = (unsigned)((rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32));
     cudaError_t e;
-    // one warp per row while a row fits 24 float4 per lane and there are enough rows to fill the GPU that way
-    if (p.max_n <= 1024 && rows >= 2048) {
+    // one warp per row when there are enough rows to fill the GPU that way and the rows are not so long that a
+    // CTA per row streams them better
+    if (p.max_n <= 8192 && rows >= 2048) {
       PdlLaunch L(dim3(warp_grid), dim3(ROW_THREADS), 0, st);
-      e = cudaLaunchKernelEx(&L.cfg, softmax_rows_warp_kernel<8>, logits, scores, cu, pcol, n_bags, T, C, Rp, rowstat, Y, wcount, n_wcount);
-    } else if (p.max_n <= 2048 && rows >= 2048) {
-      PdlLaunch L(dim3(warp_grid), dim3(ROW_THREADS), 0, st);
-      e = cudaLaunchKernelEx(&L.cfg, softmax_rows_warp_kernel<16>, logits, scores, cu, pcol, n_bags, T, C, Rp, rowstat, Y, wcount, n_wcount);
-    } else if (p.max_n <= 3072 && rows >= 2048) {
-      PdlLaunch L(dim3(warp_grid), dim3(ROW_THREADS), 0, st);
-      e = cudaLaunchKernelEx(&L.cfg, softmax_rows_warp_kernel<24>, logits, scores, cu, pcol, n_bags, T, C, Rp, rowstat, Y, wcount, n_wcount);
+      e = cudaLaunchKernelEx(&L.cfg, softmax_rows_warp_kernel, logits, scores, cu, pcol, n_bags, T, C, Rp, rowstat, Y, wcount, n_wcount);
     } else {
       PdlLaunch L(dim3((unsigned)rows), dim3(ROW_THREADS), 0, st);
       e = cudaLaunchKernelEx(&L.cfg, softmax_rows_cta_kernel, logits, scores, cu, pcol, n_bags, T, C, Rp, rowstat, Y, wcount, n_wcount);

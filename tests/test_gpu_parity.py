@@ -17,8 +17,11 @@ pytestmark = pytest.mark.gpu
 
 PROB_RTOL = 1e-3
 ATTN_ATOL = 1e-4
-# relative bounds per implementation: (attention mean, attention M2, logits abs)
-REL = {"simt_fp32": (2e-5, 2e-3, 2e-5), "tcgen05": (3e-3, 3e-2, 2e-3)}
+# relative bounds per implementation: (attention mean, attention M2 relative to its maximum, logits abs / scale).
+# About 3-6x the maxima measured over every golden case on a B200 (tools/measure_tolerances.py, round 2):
+#   simt_fp32  4.6e-7 / 1.5e-6 / 4.3e-7        tcgen05  1.0e-3 (the "peaky" x5 attention weights; 1.1e-4 at the default
+#   weights) / 6.5e-4 / 1.1e-4 — fp16 operand rounding of features and weights, tanh.approx in the epilogue.
+REL = {"simt_fp32": (5e-6, 2e-5, 5e-6), "tcgen05": (3e-3, 4e-3, 6e-4)}
 IMPLS = ["simt_fp32", "tcgen05"]
 
 
@@ -487,9 +490,16 @@ def test_feature_range_fp16_bound(mm):
         ref = G.mc_head_oracle(sd, Hn, kf, ka, 0.1, 0.1)
         res = mm.mc_head(w, torch.from_numpy(Hn).to(dev), T, seed=5, return_attention=True, validate=True)
         assert torch.isfinite(res.Y).all()
-        # saturated gates: logits are sums of +-w_c, Y scales with the features -> relative bounds
-        assert np.abs(res.A.double().cpu().numpy() - ref["A"]).max() < ATTN_ATOL
-        assert np.abs(res.Y[0].double().cpu().numpy() - ref["Y"]).max() < 2e-3 * np.abs(ref["Y"]).max()
+        # The fp16 rounding of a feature is RELATIVE (2^-11): with features of this size the pre-activations are in
+        # the hundreds, the gates saturate, and the few units near a zero crossing carry an absolute error that grows
+        # with the feature scale -> attention within ~1e-3 absolute (a few percent relative) instead of the 1e-4 / 1e-3 of
+        # O(1-10) ResNet features (the range north_star's tolerance is stated for; see DESIGN.md "Precision").
+        A, Ar = res.A.double().cpu().numpy(), ref["A"]
+        assert np.abs(A - Ar).max() < 2e-3 and np.abs(A / Ar - 1).max() < 0.1
+        assert np.abs(A.sum(-1) - 1).max() < 1e-5
+        assert np.abs(res.Y[0].double().cpu().numpy() - ref["Y"]).max() < 5e-3 * np.abs(ref["Y"]).max()
+        exact = mm.mc_head(w, torch.from_numpy(Hn).to(dev), T, seed=5, return_attention=True, impl="simt_fp32")
+        assert np.abs(exact.A.double().cpu().numpy() / Ar - 1).max() < 1e-4        # the fp32 path holds the tight bound
     Hbig = torch.from_numpy(G.make_features(900, N, scale=4e4)).to(dev)
     assert Hbig.max() > 65504
     with pytest.raises(ValueError):
