@@ -80,12 +80,6 @@ int mcmil_plan_total_rows(const mcmil_plan_t* p);
  * starts at a multiple of 32 columns; mcmil_plan_bag_plane_col returns the first column of a bag (-1: bad index). */
 int mcmil_plan_plane_cols(const mcmil_plan_t* p);
 int mcmil_plan_bag_plane_col(const mcmil_plan_t* p, int bag);
-/* Kernels the reductions behind the projection take for this plan: 1 (a cluster of 8 CTAs per bag finishes softmax,
- * pooling and the MC statistics in one launch: small batches whose per-bag slabs fit shared memory) or 2 (rows,
- * then columns).  mcmil_set_reduce_path forces one of them process-wide (0 = automatic, 1 = two launches,
- * 2 = one launch; tests and A/B measurements: both paths must agree). */
-int mcmil_plan_reduce_launches(const mcmil_plan_t* p);
-int mcmil_set_reduce_path(int path);
 
 /* ---- the hot path: model.py:280-316 + the MC statistics of infer.py:195,212-219 -------
  *   H            DEVICE fp32 [R][512] packed patch features (R = cu[n_bags])

@@ -32,8 +32,6 @@ SIGNATURES = {
     "mcmil_plan_total_rows": (_i, [_vp]),
     "mcmil_plan_plane_cols": (_i, [_vp]),
     "mcmil_plan_bag_plane_col": (_i, [_vp, _i]),
-    "mcmil_plan_reduce_launches": (_i, [_vp]),
-    "mcmil_set_reduce_path": (_i, [_i]),
     "mcmil_head_forward": (_i, [_vp, _vp, _vp, _i, _i, _u64, _i, _f, _f, _vp, _vp, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mcmil_head_forward_f16": (_i, [_vp, _vp, _vp, _i, _i, _u64, _i, _f, _f, _vp, _vp, _i,

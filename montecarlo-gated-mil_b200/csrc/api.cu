@@ -26,7 +26,6 @@ struct Profile {
   int kernels = 0;       // projection launches covered
 } g_prof;
 std::mutex g_prof_mu;
-int g_reduce_path = 0;   // mcmil_set_reduce_path (tests / A-B runs): 0 auto, 1 two launches, 2 one launch
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 int cuda_fail(cudaError_t e, const char* where) {
@@ -113,6 +112,8 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu, const int32_t* bag_
   p->R = cu[n_bags];
   p->Rw = (p->R + 31) / 32;
   std::vector<int32_t> row2bag((size_t)p->R), pcol((size_t)n_bags);
+  std::vector<int2> cblk;
+  const int tpc = col_tiles_per_cta();
   long long cols = 0;                        // every bag starts at a multiple of 32 plane columns (128 bytes)
   for (int b = 0; b < n_bags; ++b) {
     const int n = cu[b + 1] - cu[b];
@@ -125,6 +126,10 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu, const int32_t* bag_
       p->tiles.push_back(td);
     }
     for (int r = cu[b]; r < cu[b + 1]; ++r) row2bag[(size_t)r] = b;
+    {
+      const int nt = (n + TILE_ROWS - 1) / TILE_ROWS, t0 = (int)p->tiles.size() - nt;
+      for (int k = 0; k < nt; k += tpc) cblk.push_back(make_int2(t0 + k, nt - k < tpc ? nt - k : tpc));
+    }
     cols += (long long)align_up((size_t)n, 32);
   }
   if (cols > 0x7fffffffLL || (long long)T * num_classes * cols > (1LL << 40)) {
@@ -133,14 +138,16 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu, const int32_t* bag_
   }
   p->Rp = (int)cols;
   p->n_tiles = (int)p->tiles.size();
-  p->wsplit = welford_split(p->n_tiles, p->C, T);
-  p->fused_smem = fused_reduce_smem_bytes(T, p->C, p->max_n);
+  p->n_cblk = (int)cblk.size();
+  p->wsplit = welford_split(p->n_cblk, p->C, T);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = dmalloc(&p->d_cu, (size_t)n_bags + 1);
   if (e == cudaSuccess) e = dmalloc(&p->d_tiles, (size_t)p->n_tiles);
   if (e == cudaSuccess) e = dmalloc(&p->d_row2bag, (size_t)p->R);
   if (e == cudaSuccess) e = dmalloc(&p->d_gbag, (size_t)n_bags);
   if (e == cudaSuccess) e = dmalloc(&p->d_pcol, (size_t)n_bags);
+  if (e == cudaSuccess) e = dmalloc(&p->d_cblk, cblk.size());
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_cblk, cblk.data(), sizeof(int2) * cblk.size(), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_pcol, pcol.data(), sizeof(int32_t) * n_bags, cudaMemcpyHostToDevice, st);
   std::vector<int32_t> gbag((size_t)n_bags);
   for (int b = 0; b < n_bags; ++b) gbag[(size_t)b] = bag_ids ? bag_ids[b] : b;
@@ -155,7 +162,7 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu, const int32_t* bag_
   p->off_score = off;   off = align_up(off + (size_t)T * p->C * p->Rp * sizeof(float), 1024);
   p->off_rowstat = off; off = align_up(off + (size_t)T * p->C * n_bags * sizeof(float2), 1024);
   p->off_wpart = off;   off = align_up(off + (p->wsplit > 1 ? (size_t)p->wsplit * p->C * p->Rp * sizeof(float2) : 0), 1024);
-  p->off_wcount = off;  off = align_up(off + (size_t)p->n_tiles * p->C * sizeof(int), 1024);
+  p->off_wcount = off;  off = align_up(off + (size_t)p->n_cblk * p->C * sizeof(int), 1024);
   p->ws_bytes = off;
   *out = p;
   return 0;
@@ -163,7 +170,7 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu, const int32_t* bag_
 
 int mcmil_plan_destroy(mcmil_plan_t* p) {
   if (!p) return 0;
-  cudaFree(p->d_cu); cudaFree(p->d_tiles); cudaFree(p->d_row2bag); cudaFree(p->d_gbag); cudaFree(p->d_pcol);
+  cudaFree(p->d_cu); cudaFree(p->d_tiles); cudaFree(p->d_row2bag); cudaFree(p->d_gbag); cudaFree(p->d_pcol); cudaFree(p->d_cblk);
   delete p;
   return 0;
 }
@@ -175,15 +182,6 @@ int mcmil_plan_bag_plane_col(const mcmil_plan_t* p, int bag) {
   int cols = 0;
   for (int b = 0; b < bag; ++b) cols += (int)align_up((size_t)(p->cu[(size_t)b + 1] - p->cu[(size_t)b]), 32);
   return cols;
-}
-int mcmil_plan_reduce_launches(const mcmil_plan_t* p) {
-  if (!p) return 0;
-  return (g_reduce_path == 2 || (g_reduce_path == 0 && p->fused_smem != 0 && p->n_bags * 8 <= 4 * 148)) ? 1 : 2;
-}
-int mcmil_set_reduce_path(int path) {
-  if (path < 0 || path > 2) return fail(MCMIL_E_BADARG, "mcmil_set_reduce_path: 0 (auto), 1 (two launches) or 2 (one launch)");
-  g_reduce_path = path;
-  return 0;
 }
 
 static int head_forward_impl(const mcmil_weights_t* w, const mcmil_plan_t* plan, const void* H, int h_f16,
@@ -204,8 +202,6 @@ static int head_forward_impl(const mcmil_weights_t* w, const mcmil_plan_t* plan,
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023u) != 0)
     return fail(MCMIL_E_WORKSPACE, "mcmil_head_forward: workspace must be 1024-byte aligned");
   if ((reinterpret_cast<uintptr_t>(H) & 15u) != 0) return fail(MCMIL_E_BADARG, "mcmil_head_forward: H must be 16-byte aligned");
-  if (impl == MCMIL_IMPL_TCGEN05 && inj_feat == nullptr && p_f > 0.96f && p_f < 1.f)
-    return fail(MCMIL_E_UNSUPPORTED, "mcmil_head_forward: tcgen05 path supports p_f <= 0.96 or p_f == 1");
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   float* logits = reinterpret_cast<float*>(ws + plan->off_logit);
@@ -235,7 +231,7 @@ static int head_forward_impl(const mcmil_weights_t* w, const mcmil_plan_t* plan,
     return fail(MCMIL_E_BADARG, "mcmil_head_forward: unknown impl");
   }
   if (skip_reduce) return 0;
-  e = launch_reduce(*plan, logits, scores, ws, Y, A, prob_mean, prob_m2, attn_mean, attn_m2, g_reduce_path, st, &g_launches);
+  e = launch_reduce(*plan, logits, scores, ws, Y, A, prob_mean, prob_m2, attn_mean, attn_m2, st, &g_launches);
   if (e != cudaSuccess) return cuda_fail(e, "reduce");
   return 0;
 }

@@ -31,8 +31,7 @@ struct Plan {
   int Rw = 0;       // 32-bit words per row of the injected logit keep-masks: ceil(R / 32)
   int n_tiles = 0;  // 128-row pair tiles
   int max_n = 0;
-  int wsplit = 1;   // sample groups of the column-statistics kernel (generic reduction path)
-  size_t fused_smem = 0;   // dynamic shared memory of the one-launch reduction; 0 = does not fit, generic path
+  int wsplit = 1;   // sample groups of the column-statistics kernel
   std::vector<int32_t> cu;
   std::vector<TileDesc> tiles;
   int32_t* d_cu = nullptr;
@@ -40,6 +39,8 @@ struct Plan {
   int32_t* d_row2bag = nullptr;  // [R]
   int32_t* d_gbag = nullptr;     // [n_bags] global bag ids
   int32_t* d_pcol = nullptr;     // [n_bags] first plane column of each bag
+  int2* d_cblk = nullptr;        // [n_cblk] column blocks of the column kernel: (first tile, tiles in the block)
+  int n_cblk = 0;
   // workspace layout (byte offsets)
   size_t off_logit = 0, off_score = 0, off_rowstat = 0, off_wpart = 0, off_wcount = 0, ws_bytes = 0;
 };
@@ -77,13 +78,11 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
                            float* logits, float* scores, float* dbg, cudaStream_t st, int* launches);
 cudaError_t launch_proj_simt(const Weights& w, const Plan& p, const MaskSpec& m, const void* H, int h_f16,
                              float* logits, float* scores, cudaStream_t st, int* launches);
-// reduce_path: 0 = automatic (one launch when the bag slabs fit shared memory), 1 = force the generic
-// two-launch path (tests), 2 = force the one-launch path (error if it does not fit)
 cudaError_t launch_reduce(const Plan& p, const float* logits, const float* scores, uint8_t* workspace,
                           float* Y, float* A, float* prob_mean, float* prob_m2, float* attn_mean,
-                          float* attn_m2, int reduce_path, cudaStream_t st, int* launches);
-size_t fused_reduce_smem_bytes(int T, int C, int max_n);
-int welford_split(int n_tiles, int C, int T);
+                          float* attn_m2, cudaStream_t st, int* launches);
+int welford_split(int n_cblk, int C, int T);
+int col_tiles_per_cta();
 cudaError_t launch_export_masks(const Plan& p, const MaskSpec& m, uint32_t* feat_bits, uint32_t* attn_bits,
                                 cudaStream_t st);
 cudaError_t launch_attnmap(const float* A, int T, int C, int R, int row0, const int32_t* cell_ptr,

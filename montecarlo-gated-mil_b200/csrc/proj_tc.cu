@@ -169,6 +169,30 @@ __device__ __forceinline__ uint4 keep_masks(uint32_t wa, uint32_t wb, uint32_t r
   return make_uint4(keep_mask2(__byte_perm(wa, rw, s01), thr2), keep_mask2(__byte_perm(wa, rw, s23), thr2),
                     keep_mask2(__byte_perm(wb, rw, s01), thr2), keep_mask2(__byte_perm(wb, rw, s23), thr2));
 }
+// The same keep decision with ALU-pipe integer operations only (no HSET2: that shares the fmaheavy pipe with the
+// Philox wide multiplies, the busiest pipe of the kernel).  With thr = T7 * 256 + T8 (T7 = top 7 bits):
+//   keep  <=>  (P7 << 8 | R8) >= thr  <=>  P7 + [R8 >= T8] >= T7 + 1        (P7 = primary byte & 0x7f)
+// so for the four primary bytes of a word at once:  w' = (w | 0x80808080) - (T7 + 1 - c) * 0x01010101, c = [R8 >= T8];
+// every byte stays in [0, 255] (no borrow crosses bytes) and its top bit is the keep flag, which one PRMT with sign
+// replication turns into the 16-bit lane masks.  The flags c of the 16 (row slot, slice) chunks of a sample come
+// from the refinement words the same way, on 16-bit fields: byte 1 / byte 3 of fx = c of this team's slices 0 / 2,
+// of fy = c of slices 1 / 3.  Bit-identical to keep_masks() for every threshold (also thr > 0x7c00, which the fp16
+// compare cannot represent: no p_f restriction on this path).
+__device__ __forceinline__ void ref_flags(uint32_t rw, uint32_t t8x2, uint32_t& fx, uint32_t& fy) {
+  fx = ((rw & 0x00FF00FFu) | 0x01000100u) - t8x2;
+  fy = (((rw >> 8) & 0x00FF00FFu) | 0x01000100u) - t8x2;
+}
+template <int SI>
+__device__ __forceinline__ uint4 keep_masks_int(uint32_t wa, uint32_t wb, uint32_t fx, uint32_t fy, uint32_t neg_d) {
+  const uint32_t cc = __byte_perm((SI & 1) ? fy : fx, 0u, (SI & 2) ? 0x3333u : 0x1111u);      // c * 0x01010101
+  const uint32_t a = (wa | 0x80808080u) + neg_d + cc, b = (wb | 0x80808080u) + neg_d + cc;
+  uint4 m;
+  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(m.x) : "r"(a));       // features 0, 1: top bit of byte 0 / 1 over a 16-bit lane
+  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(m.y) : "r"(a));       // features 2, 3
+  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(m.z) : "r"(b));       // features 4, 5
+  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(m.w) : "r"(b));       // features 6, 7
+  return m;
+}
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -409,7 +433,12 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
     // thread-constant addresses, pinned in registers (see ptx::pin)
     const uint32_t full_team = pin(mapa(bar_addr(sbase, B_FULL), 0) + (uint32_t)team * 8u);    // + (set + TEAMS*si) * 8
     const uint32_t empty_team = pin(bar_addr(sbase, B_EMPTY) + (uint32_t)team * 8u);
+#ifdef MCMIL_MASK_HSET2
     const uint32_t thr2 = pin(P.thr_f | (P.thr_f << 16));
+#else
+    const uint32_t neg_d = pin(0u - ((P.thr_f >> 8) + 1u) * 0x01010101u);     // -(T7 + 1) in every byte
+    const uint32_t t8x2 = pin((P.thr_f & 0xFFu) * 0x00010001u);
+#endif
     const int chunk = lane & 7;
     const uint32_t q0 = pin((uint32_t)(team * 8 + chunk));       // Philox chunk index of this thread in slice `team`
     const uint32_t lane0 = pin(lane == 0 ? 1u : 0u);
@@ -478,9 +507,16 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       static_assert(!DRAW || (TEAMS == 2 && TEAM_SLICES == 4), "refinement-byte indexing assumes two producer teams");
       uint4 rnd[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};   // primary bytes: [0] row slots 0 (x,y) | 1 (z,w), [1] slots 2 | 3
       uint4 ref = make_uint4(0, 0, 0, 0);                                // word i: row slot i, byte si: this team's si-th slice
+#ifndef MCMIL_MASK_HSET2
+      uint32_t fx[4] = {0, 0, 0, 0}, fy[4] = {0, 0, 0, 0};               // [R8 >= T8] flags of the sample's 16 chunks (ref_flags)
+#endif
       if constexpr (DRAW) {
         const uint32_t tg0 = (uint32_t)(P.t_offset + t_begin);
         ref = philox4x32<ROUNDS>(REF_CHUNK_BASE + q0, nrow[0], tg0, bag, P.key);
+#ifndef MCMIL_MASK_HSET2
+        ref_flags(ref.x, t8x2, fx[0], fy[0]); ref_flags(ref.y, t8x2, fx[1], fy[1]);
+        ref_flags(ref.z, t8x2, fx[2], fy[2]); ref_flags(ref.w, t8x2, fx[3], fy[3]);
+#endif
         rnd[0] = philox4x32<ROUNDS>(q0, nrow[0], tg0, bag, P.key);
         rnd[1] = philox4x32<ROUNDS>(q0, nrow[2], tg0, bag, P.key);
       }
@@ -519,12 +555,17 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
             uint4 m;                                             // lane-pair keep masks of this (row slot, chunk)
             if constexpr (DRAW) {
               const uint32_t wa = (i & 1) ? rnd[i >> 1].z : rnd[i >> 1].x, wb = (i & 1) ? rnd[i >> 1].w : rnd[i >> 1].y;
+#ifdef MCMIL_MASK_HSET2
               const uint32_t rw = i == 0 ? ref.x : i == 1 ? ref.y : i == 2 ? ref.z : ref.w;
 #ifdef MCMIL_EXP_NO_MASK
               m = make_uint4(~0u, ~0u, ~0u, ~0u);
               asm volatile("" :: "r"(wa), "r"(wb), "r"(rw));
 #else
               m = keep_masks(wa, wb, rw, si, thr2);
+#endif
+#else
+              m = si == 0 ? keep_masks_int<0>(wa, wb, fx[i], fy[i], neg_d) : si == 1 ? keep_masks_int<1>(wa, wb, fx[i], fy[i], neg_d)
+                : si == 2 ? keep_masks_int<2>(wa, wb, fx[i], fy[i], neg_d) : keep_masks_int<3>(wa, wb, fx[i], fy[i], neg_d);
 #endif
             } else {
               const int trow = (int)rank * HALF_ROWS + rowi[i];
@@ -563,7 +604,17 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
           __syncwarp();
           if (lane0) mbar_arrive_cluster(full_team + (full_set + TEAMS * si) * 8);
           TRACE(tc, 4 * si + 3);
-          if constexpr (DRAW) { rnd[0] = nxt[0]; rnd[1] = nxt[1]; ref = ref_nxt; }
+          if constexpr (DRAW) {
+            rnd[0] = nxt[0]; rnd[1] = nxt[1];
+#ifdef MCMIL_MASK_HSET2
+            ref = ref_nxt;
+#else
+            if (si == TEAM_SLICES - 1) {             // the next sample's refinement words were just drawn
+              ref_flags(ref_nxt.x, t8x2, fx[0], fy[0]); ref_flags(ref_nxt.y, t8x2, fx[1], fy[1]);
+              ref_flags(ref_nxt.z, t8x2, fx[2], fy[2]); ref_flags(ref_nxt.w, t8x2, fx[3], fy[3]);
+            }
+#endif
+          }
         }
       }
       u = u_next < u_end ? u_next : u_end;

@@ -129,15 +129,6 @@ def _check_cu(what: str, cu_seqlens, R: int) -> np.ndarray:
     return cu.astype(np.int32)
 
 
-def set_reduce_path(path: str = "auto") -> None:
-    """Tests / A-B measurements: force the reductions behind the projection onto the one-launch ("fused") or the
-    two-launch ("split") path; "auto" (default) picks per plan.  Both paths compute the same outputs."""
-    code = {"auto": 0, "split": 1, "fused": 2}.get(path)
-    if code is None:
-        raise ValueError("set_reduce_path: auto / split / fused")
-    _lib.check(_lib.load().mcmil_set_reduce_path(code), "mcmil_set_reduce_path")
-
-
 def _get_plan(cu: np.ndarray, T: int, C_: int, device, bag_ids=None) -> _Plan:
     ids_key = None if bag_ids is None else np.asarray(bag_ids, np.int32).tobytes()
     key = (cu.tobytes(), ids_key, int(T), int(C_), str(device))

@@ -124,70 +124,50 @@ def test_golden_injected_masks(mm, name, impl):
     _check(res, c.ref, impl, c.T, A_ref=c.ref["A"].astype(np.float64), A_stride=c.A_stride)
 
 
-@pytest.fixture
-def reduce_path(mm, request):
-    """Force the reductions onto the one-launch ("fused") or the two-launch ("split") path for one test."""
-    mm.set_reduce_path(request.param)
-    yield request.param
-    mm.set_reduce_path("auto")
-
-
-@pytest.mark.parametrize("reduce_path", ["auto", "split"], indirect=True)
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("name", [n for n in golden_names() if not n.endswith("native")])
-def test_golden_inkernel_philox(mm, name, impl, reduce_path):
+def test_golden_inkernel_philox(mm, name, impl):
     """Same cases with the masks drawn by the in-kernel Philox (no injection): must land on the
-    same reference outputs, because the golden masks ARE that Philox stream.  Run on both reduction paths
-    ("auto" takes the one-launch path at these sizes, "split" the two-launch one)."""
+    same reference outputs, because the golden masks ARE that Philox stream."""
     c = Case(name)
     dev = torch.device("cuda")
     w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in c.sd.items()}, dev)
     H = torch.from_numpy(c.H).to(dev)
     res = mm.mc_head(w, H, c.T, seed=c.mseed, p_f=c.p_f, p_a=c.p_a, t_offset=c.t0, bag_offset=c.bag,
                      return_attention=True, impl=impl)
-    assert res.launches == (1 if c.shared else c.C) + (2 if reduce_path == "split" else 1) or impl != "tcgen05"
+    assert res.launches == (1 if c.shared else c.C) + 2        # projection launch(es) + rows + columns
     _check(res, c.ref, impl, c.T, A_ref=c.ref["A"].astype(np.float64), A_stride=c.A_stride)
 
 
-def test_reduce_paths_agree(mm):
-    """One-launch (cluster of 8 CTAs per bag, slabs in shared memory, DSMEM exchange) vs two-launch (rows, then
-    columns with the samples split over CTAs) reductions on the same projection output: every output agrees to
-    fp32 summation-order rounding; both are run-to-run deterministic."""
+def test_reduction_dispatch_variants_agree(mm):
+    """The row kernel has three forms (warp per row in one chunk / in 1024-patch chunks merged on the fly / CTA per
+    row) and the column kernel splits the MC samples over 1..16 CTAs per tile; which one runs depends on the batch
+    shape.  The same bags packed into batches that select different forms give the same outputs up to fp32
+    summation-order rounding, and every form is run-to-run deterministic."""
     dev = torch.device("cuda")
-    sd3 = G.make_weights(71, 3, False)
-    sd2 = G.make_weights(72, 2, True)
-    cases = [(sd2, [1024], 100), (sd2, [200, 77, 333, 1, 128, 129, 64, 5], 9), (sd3, [130, 7], 1), (sd2, [3000], 20),
-             (sd2, [40] * 40, 12)]
-    for sd, lens, T in cases:
-        w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
-        cu = np.concatenate([[0], np.cumsum(lens)])
-        g = torch.Generator(device=dev).manual_seed(len(lens))
-        H = torch.relu(torch.randn(int(cu[-1]), 512, generator=g, device=dev))
-        out = {}
-        for path in ("fused", "split"):
-            mm.set_reduce_path(path)
-            try:
-                out[path] = mm.mc_head(w, H, T, seed=3, cu_seqlens=cu, return_attention=True)
-                again = mm.mc_head(w, H, T, seed=3, cu_seqlens=cu, return_attention=True)
-            finally:
-                mm.set_reduce_path("auto")
-            assert torch.equal(out[path].Y, again.Y) and torch.equal(out[path].attn_m2, again.attn_m2)
-        a, b = out["fused"], out["split"]
-        assert a.launches == b.launches - 1
-        assert (a.Y - b.Y).abs().max().item() <= 2e-6 * max(1.0, b.Y.abs().max().item())
-        assert (a.A / b.A - 1).abs().max().item() < 2e-6
-        assert (a.attn_mean / b.attn_mean - 1).abs().max().item() < 2e-6
-        assert (a.attn_m2 - b.attn_m2).abs().max().item() <= 1e-5 * b.attn_m2.abs().max().item() + 1e-12
-        assert (a.prob_mean - b.prob_mean).abs().max().item() < 1e-6
-        assert (a.prob_m2 - b.prob_m2).abs().max().item() <= 1e-5 * max(1.0, b.prob_m2.abs().max().item())
-    # a bag whose slabs do not fit shared memory cannot be forced onto the one-launch path
-    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd2.items()}, dev)
-    mm.set_reduce_path("fused")
-    try:
-        with pytest.raises(RuntimeError):
-            mm.mc_head(w, torch.zeros(16384, 512, device=dev), 64)
-    finally:
-        mm.set_reduce_path("auto")
+    sd = G.make_weights(72, 2, True)
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
+    T = 40
+    lens = [700, 1500, 90]
+    g = torch.Generator(device=dev).manual_seed(5)
+    Hs = [torch.relu(torch.randn(n, 512, generator=g, device=dev)) for n in lens]
+    # (a) each bag alone: few rows -> CTA-per-row kernel, samples split over several CTAs per tile
+    alone = [mm.mc_head(w, h, T, seed=3, bag_ids=[i], return_attention=True) for i, h in enumerate(Hs)]
+    # (b) packed together with enough filler bags that the warp-per-row kernel (chunked: max_n > 1024) runs
+    fill = [torch.relu(torch.randn(64, 512, generator=g, device=dev)) for _ in range(30)]
+    allb = Hs + fill
+    cu = np.concatenate([[0], np.cumsum([int(h.shape[0]) for h in allb])])
+    packed = mm.mc_head(w, torch.cat(allb), T, seed=3, cu_seqlens=cu, bag_ids=list(range(len(allb))), return_attention=True)
+    again = mm.mc_head(w, torch.cat(allb), T, seed=3, cu_seqlens=cu, bag_ids=list(range(len(allb))), return_attention=True)
+    assert torch.equal(packed.Y, again.Y) and torch.equal(packed.attn_m2, again.attn_m2) and torch.equal(packed.A, again.A)
+    for i, a in enumerate(alone):
+        sl = slice(int(cu[i]), int(cu[i + 1]))
+        assert (a.Y[0] - packed.Y[i]).abs().max().item() <= 2e-6 * max(1.0, packed.Y.abs().max().item())
+        assert (a.A / packed.A[:, :, sl] - 1).abs().max().item() < 3e-6
+        assert (a.attn_mean / packed.attn_mean[:, sl] - 1).abs().max().item() < 3e-6
+        assert (a.attn_m2 - packed.attn_m2[:, sl]).abs().max().item() <= 2e-5 * a.attn_m2.abs().max().item() + 1e-12
+        assert (a.prob_mean[0] - packed.prob_mean[i]).abs().max().item() < 1e-6
+        assert (a.prob_m2[0] - packed.prob_m2[i]).abs().max().item() <= 1e-5 * max(1.0, a.prob_m2.abs().max().item())
 
 
 @pytest.mark.parametrize("impl", IMPLS)
