@@ -112,7 +112,7 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu, const int32_t* bag_
   p->R = cu[n_bags];
   p->Rw = (p->R + 31) / 32;
   std::vector<int32_t> row2bag((size_t)p->R), pcol((size_t)n_bags);
-  std::vector<int2> cblk;
+  std::vector<int4> cblk;
   const int tpc = col_tiles_per_cta();
   long long cols = 0;                        // every bag starts at a multiple of 32 plane columns (128 bytes)
   for (int b = 0; b < n_bags; ++b) {
@@ -126,16 +126,15 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu, const int32_t* bag_
       p->tiles.push_back(td);
     }
     for (int r = cu[b]; r < cu[b + 1]; ++r) row2bag[(size_t)r] = b;
-    {
-      const int nt = (n + TILE_ROWS - 1) / TILE_ROWS, t0 = (int)p->tiles.size() - nt;
-      for (int k = 0; k < nt; k += tpc) cblk.push_back(make_int2(t0 + k, nt - k < tpc ? nt - k : tpc));
-    }
+    for (int n0 = 0; n0 < n; n0 += tpc * TILE_ROWS)          // column blocks: up to tpc consecutive tiles of the bag
+      cblk.push_back(make_int4((int)cols + n0, cu[b] + n0, b, n - n0 < tpc * TILE_ROWS ? n - n0 : tpc * TILE_ROWS));
     cols += (long long)align_up((size_t)n, 32);
   }
   if (cols > 0x7fffffffLL || (long long)T * num_classes * cols > (1LL << 40)) {
     delete p;
     return fail(MCMIL_E_UNSUPPORTED, "mcmil_plan_create: batch too large for one call");
   }
+  if (cols > 0x7fffffffLL) { delete p; return fail(MCMIL_E_UNSUPPORTED, "mcmil_plan_create: batch too large for one call"); }
   p->Rp = (int)cols;
   p->n_tiles = (int)p->tiles.size();
   p->n_cblk = (int)cblk.size();
@@ -147,7 +146,7 @@ int mcmil_plan_create(mcmil_plan_t** out, const int32_t* cu, const int32_t* bag_
   if (e == cudaSuccess) e = dmalloc(&p->d_gbag, (size_t)n_bags);
   if (e == cudaSuccess) e = dmalloc(&p->d_pcol, (size_t)n_bags);
   if (e == cudaSuccess) e = dmalloc(&p->d_cblk, cblk.size());
-  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_cblk, cblk.data(), sizeof(int2) * cblk.size(), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_cblk, cblk.data(), sizeof(int4) * cblk.size(), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_pcol, pcol.data(), sizeof(int32_t) * n_bags, cudaMemcpyHostToDevice, st);
   std::vector<int32_t> gbag((size_t)n_bags);
   for (int b = 0; b < n_bags; ++b) gbag[(size_t)b] = bag_ids ? bag_ids[b] : b;

@@ -39,7 +39,7 @@ struct Plan {
   int32_t* d_row2bag = nullptr;  // [R]
   int32_t* d_gbag = nullptr;     // [n_bags] global bag ids
   int32_t* d_pcol = nullptr;     // [n_bags] first plane column of each bag
-  int2* d_cblk = nullptr;        // [n_cblk] column blocks of the column kernel: (first tile, tiles in the block)
+  int4* d_cblk = nullptr;        // [n_cblk] column blocks of the column kernel: (plane column, packed row, bag, patches)
   int n_cblk = 0;
   // workspace layout (byte offsets)
   size_t off_logit = 0, off_score = 0, off_rowstat = 0, off_wpart = 0, off_wcount = 0, ws_bytes = 0;

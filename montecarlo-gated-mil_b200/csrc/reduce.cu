@@ -257,7 +257,7 @@ constexpr int COL_TGROUPS = COL_WARPS / COL_TPC;   // the CTA's samples are stri
 constexpr int COL_UNROLL = MCMIL_COL_UNROLL;
 constexpr int COL_MAX_SPLIT = 16;
 constexpr int COL_KPT = (COL_TPC * TILE_ROWS + COL_THREADS - 1) / COL_THREADS;   // patches per thread in the final merge
-static_assert(COL_LANES * COL_VEC == TILE_ROWS && (COL_TPC == 1 || COL_TPC == 2 || COL_TPC == 4), "column CTA shape");
+static_assert(COL_LANES * COL_VEC == TILE_ROWS && (COL_TPC == 1 || COL_TPC == 2 || COL_TPC == 4 || COL_TPC == 8), "column CTA shape");
 int col_tiles_per_cta() { return COL_TPC; }
 
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
@@ -294,7 +294,7 @@ __device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
 template <bool HAS_A>
 __global__ void __launch_bounds__(COL_THREADS, MCMIL_COL_MINB)
 welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__ rowstat,
-                    const TileDesc* __restrict__ tiles, const int2* __restrict__ cblk, const float* __restrict__ Y,
+                    const int4* __restrict__ cblk, const float* __restrict__ Y,
                     int n_bags, int T, int C, int R, int Rp, int n_cblk, int wsplit,
                     float2* __restrict__ wpart, int* __restrict__ wcount,
                     float* __restrict__ A, float* __restrict__ attn_mean, float* __restrict__ attn_m2,
@@ -311,11 +311,9 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
   __shared__ float s_mean[COL_TGROUPS][COL_TPC * TILE_ROWS], s_m2[COL_TGROUPS][COL_TPC * TILE_ROWS];
   __shared__ int s_cnt[COL_WARPS];
   __shared__ int s_last;
-  const int2 blk = cblk[blockIdx.x];                         // (first tile, tiles in this block)
+  const int4 blk = cblk[blockIdx.x];                         // one load: (plane column, packed row, bag, patches) of the block
   const int cg = warp % COL_TPC, grp = warp / COL_TPC;
-  const TileDesc* td0 = tiles + blk.x;
-  const int pcol_b = td0->pcol0, row_b = td0->row0, bag = td0->bag;
-  const int ncols_b = (blk.y - 1) * TILE_ROWS + td0[blk.y - 1].nrows;       // patches of the block
+  const int pcol_b = blk.x, row_b = blk.y, bag = blk.z, ncols_b = blk.w;
   const int c = blockIdx.y, z = blockIdx.z;
   const int t_lo = (int)((long long)T * z / wsplit), t_hi = (int)((long long)T * (z + 1) / wsplit);
   // (the last 16-byte load of the block may reach into the bag's plane padding: loaded, its results never stored)
@@ -324,59 +322,70 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
   const size_t tstride = (size_t)C * Rp;
   const float2* rs_row = rowstat + ((size_t)c * n_bags + bag) * T;
   uint64_t mean01 = 0ull, mean23 = 0ull, q01 = 0ull, q23 = 0ull;
-  int cnt = 0;
+  float cntf = 0.f;
   constexpr float LOG2E = 1.4426950408889634f;
-  if (col_w < ncols_b) {
-    for (int t = t_lo + grp; t < t_hi; t += COL_TGROUPS * COL_UNROLL) {
+  // one sample of this lane's 4 patches: a = 2^(l log2e - max log2e) / sum, then Welford, two patches per instruction
+  auto push = [&](const float4& l4, const float2& rs, int tu) {
+    const float nm = -rs.x * LOG2E;
+    const uint64_t k2 = f2_pack(LOG2E, LOG2E), nm2 = f2_pack(nm, nm), inv2 = f2_pack(rs.y, rs.y);
+    float x0, x1, x2, x3;
+    f2_unpack(f2_fma(f2_pack(l4.x, l4.y), k2, nm2), x0, x1);
+    f2_unpack(f2_fma(f2_pack(l4.z, l4.w), k2, nm2), x2, x3);
+    float e0, e1, e2, e3;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(x2));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(x3));
+    const uint64_t a01 = f2_mul(f2_pack(e0, e1), inv2), a23 = f2_mul(f2_pack(e2, e3), inv2);
+    if constexpr (HAS_A) {
+      float a0, a1, a2, a3;
+      f2_unpack(a01, a0, a1);
+      f2_unpack(a23, a2, a3);
+      float* dst = A + ((size_t)tu * C + c) * R + row_b + col_w;
+      const int left = ncols_b - col_w;
+      dst[0] = a0;
+      if (left > 1) dst[1] = a1;
+      if (left > 2) dst[2] = a2;
+      if (left > 3) dst[3] = a3;
+    }
+    cntf += 1.0f;
+    const float ic = fast_rcp(cntf);
+    const uint64_t ic2 = f2_pack(ic, ic);
+    const uint64_t d01 = f2_sub(a01, mean01), d23 = f2_sub(a23, mean23);
+    mean01 = f2_fma(d01, ic2, mean01);
+    mean23 = f2_fma(d23, ic2, mean23);
+    q01 = f2_fma(d01, f2_sub(a01, mean01), q01);
+    q23 = f2_fma(d23, f2_sub(a23, mean23), q23);
+  };
+  const int n_my = col_w < ncols_b ? (t_hi - t_lo - grp + COL_TGROUPS - 1) / COL_TGROUPS : 0;   // this warp's samples
+  if (n_my > 0) {
+    // pointer-increment addressing: the COL_UNROLL loads of a batch only differ by compile-time multiples of one
+    // 64-bit step, so they are issued back to back (index arithmetic between the loads serialised them on the
+    // scoreboard: profiles/r2_experiments.md)
+    const float4* lp = reinterpret_cast<const float4*>(plane + (size_t)(t_lo + grp) * tstride);
+    const size_t step = (size_t)COL_TGROUPS * (tstride / 4);           // float4 units (Rp is a multiple of 32)
+    const float2* rp = rs_row + t_lo + grp;
+    int tu = t_lo + grp, i = 0;
+    for (; i + COL_UNROLL <= n_my; i += COL_UNROLL) {
       float4 l4[COL_UNROLL];
       float2 rs[COL_UNROLL];
 #pragma unroll
-      for (int u = 0; u < COL_UNROLL; ++u) {
-        const int tu = t + u * COL_TGROUPS;
-        if (tu < t_hi) {
-          l4[u] = __ldg(reinterpret_cast<const float4*>(plane + (size_t)tu * tstride));
-          rs[u] = __ldg(rs_row + tu);
-        }
-      }
+      for (int u = 0; u < COL_UNROLL; ++u) { l4[u] = __ldg(lp + u * step); rs[u] = __ldg(rp + u * COL_TGROUPS); }
+      lp += COL_UNROLL * step;
+      rp += COL_UNROLL * COL_TGROUPS;
 #pragma unroll
-      for (int u = 0; u < COL_UNROLL; ++u) {
-        const int tu = t + u * COL_TGROUPS;
-        if (tu < t_hi) {
-          // a = 2^(l log2e - max log2e) / sum, two patches per instruction
-          const float nm = -rs[u].x * LOG2E;
-          const uint64_t k2 = f2_pack(LOG2E, LOG2E), nm2 = f2_pack(nm, nm), inv2 = f2_pack(rs[u].y, rs[u].y);
-          float x0, x1, x2, x3;
-          f2_unpack(f2_fma(f2_pack(l4[u].x, l4[u].y), k2, nm2), x0, x1);
-          f2_unpack(f2_fma(f2_pack(l4[u].z, l4[u].w), k2, nm2), x2, x3);
-          float e0, e1, e2, e3;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(x2));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(x3));
-          const uint64_t a01 = f2_mul(f2_pack(e0, e1), inv2), a23 = f2_mul(f2_pack(e2, e3), inv2);
-          if constexpr (HAS_A) {
-            float a0, a1, a2, a3;
-            f2_unpack(a01, a0, a1);
-            f2_unpack(a23, a2, a3);
-            float* dst = A + ((size_t)tu * C + c) * R + row_b + col_w;
-            const int left = ncols_b - col_w;
-            dst[0] = a0;
-            if (left > 1) dst[1] = a1;
-            if (left > 2) dst[2] = a2;
-            if (left > 3) dst[3] = a3;
-          }
-          ++cnt;
-          const float ic = fast_rcp((float)cnt);
-          const uint64_t ic2 = f2_pack(ic, ic);
-          const uint64_t d01 = f2_sub(a01, mean01), d23 = f2_sub(a23, mean23);
-          mean01 = f2_fma(d01, ic2, mean01);
-          mean23 = f2_fma(d23, ic2, mean23);
-          q01 = f2_fma(d01, f2_sub(a01, mean01), q01);
-          q23 = f2_fma(d23, f2_sub(a23, mean23), q23);
-        }
-      }
+      for (int u = 0; u < COL_UNROLL; ++u) push(l4[u], rs[u], tu + u * COL_TGROUPS);
+      tu += COL_UNROLL * COL_TGROUPS;
+    }
+    for (; i < n_my; ++i) {
+      const float4 l4 = __ldg(lp);
+      const float2 rs = __ldg(rp);
+      lp += step; rp += COL_TGROUPS;
+      push(l4, rs, tu);
+      tu += COL_TGROUPS;
     }
   }
+  const int cnt = n_my;
   {
     float m0, m1, m2_, m3, v0, v1, v2, v3;
     f2_unpack(mean01, m0, m1); f2_unpack(mean23, m2_, m3);
@@ -437,12 +446,18 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
 }
 
 int welford_split(int n_cblk, int C, int T) {
-  // enough CTAs for ~4 per SM when there are few column blocks (one large bag), at least 16 samples per group
-  const long long ctas = (long long)n_cblk * C;
-  long long s = (592 + ctas - 1) / ctas;
-  if (s > COL_MAX_SPLIT) s = COL_MAX_SPLIT;
-  if (s > T / 16) s = T / 16;
-  return s < 1 ? 1 : (int)s;
+  // Sample groups per (column block, head): the kernel runs 4 CTAs per SM, so a grid just above a multiple of the
+  // 592 CTA slots of a B200 pays a whole extra wave (one bag of 16384 patches at T = 1000: 640 CTAs took two waves,
+  // 51 % of the copy peak).  Pick the split that minimises waves x samples per CTA (plus one unit per group for the
+  // partial write and merge), at least 16 samples per group.
+  const long long ctas = (long long)n_cblk * C, slots = 4 * 148;
+  long long best = 1, best_cost = -1;
+  for (long long s = 1; s <= COL_MAX_SPLIT && (s == 1 || s <= T / 16); ++s) {
+    const long long waves = (ctas * s + slots - 1) / slots;
+    const long long cost = waves * ((T + s - 1) / s + (s > 1 ? 2 : 0));
+    if (best_cost < 0 || cost < best_cost) { best = s; best_cost = cost; }
+  }
+  return (int)best;
 }
 
 cudaError_t launch_reduce(const Plan& p, const float* logits, const float* scores, uint8_t* workspace,
@@ -478,14 +493,13 @@ cudaError_t launch_reduce(const Plan& p, const float* logits, const float* score
   {
     PdlLaunch L(dim3(p.n_cblk + bag_blocks, p.C, p.wsplit), dim3(COL_THREADS), 0, st);
     const float2* rs = rowstat;
-    const TileDesc* tiles = p.d_tiles;
-    const int2* cblk = p.d_cblk;
+    const int4* cblk = p.d_cblk;
     const float* Yc = Y;
     int n_cblk = p.n_cblk, wsplit = p.wsplit;
     cudaError_t e = A != nullptr
-        ? cudaLaunchKernelEx(&L.cfg, welford_cols_kernel<true>, logits, rs, tiles, cblk, Yc, n_bags, T, C, R, Rp, n_cblk, wsplit,
+        ? cudaLaunchKernelEx(&L.cfg, welford_cols_kernel<true>, logits, rs, cblk, Yc, n_bags, T, C, R, Rp, n_cblk, wsplit,
                              wpart, wcount, A, attn_mean, attn_m2, prob_mean, prob_m2)
-        : cudaLaunchKernelEx(&L.cfg, welford_cols_kernel<false>, logits, rs, tiles, cblk, Yc, n_bags, T, C, R, Rp, n_cblk, wsplit,
+        : cudaLaunchKernelEx(&L.cfg, welford_cols_kernel<false>, logits, rs, cblk, Yc, n_bags, T, C, R, Rp, n_cblk, wsplit,
                              wpart, wcount, A, attn_mean, attn_m2, prob_mean, prob_m2);
     if (e != cudaSuccess) return e;
   }
