@@ -79,6 +79,11 @@ int mcmil_plan_total_rows(const mcmil_plan_t* p);
 /* Layout of the internal logit / score planes [T][C][plane_cols] (what mcmil_debug_proj_tc copies out): every bag
  * starts at a multiple of 32 columns; mcmil_plan_bag_plane_col returns the first column of a bag (-1: bad index). */
 int mcmil_plan_plane_cols(const mcmil_plan_t* p);
+/* Limits the projection kernel of calls with this plan to `sms` streaming multiprocessors (0 = all; rounded down to
+ * CTA pairs, at least one).  Several single-bag calls issued on DIFFERENT streams then run side by side, each on its
+ * share of the GPU, and the fixed per-kernel cost of one call (prologue, pipeline fill, tail: ~10 of ~33 us for one
+ * bag of 1024 patches, T = 100) overlaps with the steady state of the others.  Results do not depend on the limit. */
+int mcmil_plan_set_sm_limit(mcmil_plan_t* p, int sms);
 int mcmil_plan_bag_plane_col(const mcmil_plan_t* p, int bag);
 
 /* ---- the hot path: model.py:280-316 + the MC statistics of infer.py:195,212-219 -------

@@ -31,6 +31,7 @@ SIGNATURES = {
     "mcmil_plan_workspace_bytes": (_sz, [_vp]),
     "mcmil_plan_total_rows": (_i, [_vp]),
     "mcmil_plan_plane_cols": (_i, [_vp]),
+    "mcmil_plan_set_sm_limit": (_i, [_vp, _i]),
     "mcmil_plan_bag_plane_col": (_i, [_vp, _i]),
     "mcmil_head_forward": (_i, [_vp, _vp, _vp, _i, _i, _u64, _i, _f, _f, _vp, _vp, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -176,6 +176,11 @@ int mcmil_plan_destroy(mcmil_plan_t* p) {
 size_t mcmil_plan_workspace_bytes(const mcmil_plan_t* p) { return p ? p->ws_bytes : 0; }
 int mcmil_plan_total_rows(const mcmil_plan_t* p) { return p ? p->R : 0; }
 int mcmil_plan_plane_cols(const mcmil_plan_t* p) { return p ? p->Rp : 0; }
+int mcmil_plan_set_sm_limit(mcmil_plan_t* p, int sms) {
+  if (!p || sms < 0) return fail(MCMIL_E_BADARG, "mcmil_plan_set_sm_limit: null plan or negative limit");
+  p->sm_limit = sms;
+  return 0;
+}
 int mcmil_plan_bag_plane_col(const mcmil_plan_t* p, int bag) {
   if (!p || bag < 0 || bag >= p->n_bags) return -1;
   int cols = 0;

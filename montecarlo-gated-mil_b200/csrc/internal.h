@@ -32,6 +32,7 @@ struct Plan {
   int n_tiles = 0;  // 128-row pair tiles
   int max_n = 0;
   int wsplit = 1;   // sample groups of the column-statistics kernel
+  int sm_limit = 0; // SMs the projection kernel may use (0 = all): mcmil_plan_set_sm_limit
   std::vector<int32_t> cu;
   std::vector<TileDesc> tiles;
   int32_t* d_cu = nullptr;

@@ -779,6 +779,7 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
   }
   const long long units = (long long)p.n_tiles * p.T;
   int n_pairs = sms / 2;
+  if (p.sm_limit > 0 && p.sm_limit / 2 < n_pairs) n_pairs = p.sm_limit / 2 > 0 ? p.sm_limit / 2 : 1;
   if (units < n_pairs) n_pairs = (int)units;
   if (n_pairs < 1) return cudaSuccess;
   for (int s = 0; s < w.S; ++s) {

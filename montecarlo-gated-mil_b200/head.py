@@ -172,6 +172,7 @@ class MCHeadResult:
     count: int
     cu_seqlens: np.ndarray
     launches: int = 0
+    stream: Optional[torch.cuda.Stream] = None     # MCHeadRunner throughput mode: the stream the call runs on
 
     def prob_var(self, ddof: int = 0):      # infer.py:52 uses np.std (ddof=0)
         return self.prob_m2 / max(self.count - ddof, 1)
@@ -262,15 +263,48 @@ def mc_head(weights: HeadWeights, H: torch.Tensor, T: int, seed: int = 0,
     return MCHeadResult(Y, pm, pq, am, aq, A, T, cu, launches)
 
 
+class _RunnerSlot:
+    """One in-flight call of an MCHeadRunner: its own plan (SM limit), workspace, outputs and stream."""
+
+    def __init__(self, runner, cu, sm_limit: int, stream):
+        lib, dev, T, C_, n_rows = runner.lib, runner.dev, runner.T, runner.w.num_classes, runner.R
+        self.plan = _Plan(cu, T, C_, dev) if sm_limit else _get_plan(cu, T, C_, dev)     # a limited plan is private
+        if sm_limit:
+            _lib.check(lib.mcmil_plan_set_sm_limit(self.plan._h, int(sm_limit)), "mcmil_plan_set_sm_limit")
+        nb = self.plan.n_bags
+        with torch.cuda.device(dev):
+            f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)   # noqa: E731
+            self.Y, self.pm, self.pq = f(nb, T, C_), f(nb, C_), f(nb, C_)
+            self.am, self.aq = f(C_, n_rows), f(C_, n_rows)
+            self.A = f(T, C_, n_rows) if runner.return_attention else None
+            self.ws = torch.empty(self.plan.ws_bytes + 2048, dtype=torch.uint8, device=dev)
+        off = (-self.ws.data_ptr()) % 1024
+        self.tail = (runner.philox_rounds, runner.p_f, runner.p_a, None, None, runner.impl,
+                     _ptr(self.Y), _ptr(self.A), _ptr(self.pm), _ptr(self.pq), _ptr(self.am), _ptr(self.aq),
+                     C.c_void_p(self.ws.data_ptr() + off), self.plan.ws_bytes)
+        self.stream = stream
+        self.result = MCHeadResult(self.Y, self.pm, self.pq, self.am, self.aq, self.A, T, cu, 0)
+        self.result.stream = stream
+
+
 class MCHeadRunner:
     """Low-overhead repeated calls for ONE fixed shape (the reference's bs == 1 serving loop, infer.py:187-196):
     plan, workspace and output tensors are created once, `run(H, seed)` is a single C-ABI call (no allocation,
-    no validation beyond the shape).  The returned MCHeadResult aliases the runner's buffers: it is valid until
-    the next `run`.  Same kernels and results as `mc_head`."""
+    no validation beyond the shape).  Same kernels and results as `mc_head`.
+
+    n_streams = 1 (default): every call runs on the caller's current stream; the returned MCHeadResult aliases the
+    runner's buffers and is valid until the next `run`.
+
+    n_streams = k > 1 (throughput mode): consecutive calls go round-robin to k private streams, each with its own
+    buffers, and the projection kernel of a call is limited to 1/k of the SMs (`mcmil_plan_set_sm_limit`), so k bags
+    are in flight side by side and the fixed per-kernel cost of a single-bag call (~10 of ~33 us) overlaps with the
+    other bags' steady state.  Per-bag latency grows ~k times, bags/s approach the packed-batch rate.  The result
+    of a call is valid until k further calls; wait for it with `result.stream.synchronize()` (or `synchronize()`
+    for all), the input H must stay untouched until then."""
 
     def __init__(self, weights: HeadWeights, n_rows: int, T: int, p_f: float = 0.1, p_a: float = 0.1,
                  cu_seqlens: Optional[Sequence[int]] = None, return_attention: bool = False,
-                 philox_rounds: int = 10, impl: str = "tcgen05"):
+                 philox_rounds: int = 10, impl: str = "tcgen05", n_streams: int = 1):
         self.lib = _lib.load()
         self.w, self.dev, self.T, self.R = weights, weights.device, int(T), int(n_rows)
         if impl not in _lib.IMPLS:
@@ -279,31 +313,44 @@ class MCHeadRunner:
             raise ValueError("MCHeadRunner: T and n_rows must be >= 1")
         if philox_rounds not in (7, 10) or not (0.0 <= p_f <= 1.0 and 0.0 <= p_a <= 1.0):
             raise ValueError("MCHeadRunner: philox_rounds must be 10 or 7 and the dropout probabilities in [0, 1]")
+        if not 1 <= int(n_streams) <= 16:
+            raise ValueError("MCHeadRunner: n_streams must be in [1, 16]")
         cu = _check_cu("MCHeadRunner", cu_seqlens, int(n_rows))
-        C_ = weights.num_classes
-        self.plan = _get_plan(cu, T, C_, self.dev)
-        nb = self.plan.n_bags
-        with torch.cuda.device(self.dev):
-            f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.dev)   # noqa: E731
-            self.Y, self.pm, self.pq = f(nb, T, C_), f(nb, C_), f(nb, C_)
-            self.am, self.aq = f(C_, n_rows), f(C_, n_rows)
-            self.A = f(T, C_, n_rows) if return_attention else None
-            self.ws = torch.empty(self.plan.ws_bytes + 2048, dtype=torch.uint8, device=self.dev)
-        off = (-self.ws.data_ptr()) % 1024
-        self._tail = (int(philox_rounds), float(p_f), float(p_a), None, None, _lib.IMPLS[impl],
-                      _ptr(self.Y), _ptr(self.A), _ptr(self.pm), _ptr(self.pq), _ptr(self.am), _ptr(self.aq),
-                      C.c_void_p(self.ws.data_ptr() + off), self.plan.ws_bytes)
-        self.result = MCHeadResult(self.Y, self.pm, self.pq, self.am, self.aq, self.A, self.T, cu, 0)
+        self.philox_rounds, self.p_f, self.p_a, self.impl = int(philox_rounds), float(p_f), float(p_a), _lib.IMPLS[impl]
+        self.return_attention = bool(return_attention)
+        self.n_streams = int(n_streams)
+        if self.n_streams == 1:
+            self.slots = [_RunnerSlot(self, cu, 0, None)]
+        else:
+            sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+            share = max(2, (sms // self.n_streams) & ~1)
+            with torch.cuda.device(self.dev):
+                self.slots = [_RunnerSlot(self, cu, share, torch.cuda.Stream(self.dev)) for _ in range(self.n_streams)]
+        self._next = 0
+        self.plan = self.slots[0].plan
+        self.result = self.slots[0].result
 
     def run(self, H: torch.Tensor, seed: int = 0, t_offset: int = 0, bag_offset: int = 0) -> MCHeadResult:
         if H.device != self.dev or H.dtype != torch.float32 or tuple(H.shape) != (self.R, L_FEAT) or not H.is_contiguous():
             raise ValueError(f"MCHeadRunner.run: H must be a contiguous float32 ({self.R}, {L_FEAT}) tensor on {self.dev}")
-        code = self.lib.mcmil_head_forward(self.w._h, self.plan._h, C.c_void_p(H.data_ptr()), int(t_offset),
-                                           int(bag_offset), int(seed) & 0xFFFFFFFFFFFFFFFF, *self._tail,
-                                           C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream))
+        slot = self.slots[self._next]
+        if self.n_streams == 1:
+            stream = torch.cuda.current_stream(self.dev).cuda_stream
+        else:
+            self._next = (self._next + 1) % self.n_streams
+            slot.stream.wait_stream(torch.cuda.current_stream(self.dev))       # H was produced on the caller's stream
+            stream = slot.stream.cuda_stream
+        code = self.lib.mcmil_head_forward(self.w._h, slot.plan._h, C.c_void_p(H.data_ptr()), int(t_offset),
+                                           int(bag_offset), int(seed) & 0xFFFFFFFFFFFFFFFF, *slot.tail,
+                                           C.c_void_p(stream))
         if code:
             _lib.check(code, "mcmil_head_forward")
-        return self.result
+        return slot.result
+
+    def synchronize(self):
+        """Wait for every call issued so far (throughput mode: all private streams)."""
+        for slot in self.slots:
+            (slot.stream or torch.cuda.current_stream(self.dev)).synchronize()
 
 
 def head_forward_eval(weights: HeadWeights, H: torch.Tensor, cu_seqlens: Optional[Sequence[int]] = None,
