@@ -18,7 +18,8 @@ around it, live), `cpu_baseline` = the reference's CPU path on this host.  Extra
 `separate` (shared_attention=False, the reference's YAML default), `config3` (256 ragged bags,
 LPT bag sharding, strong scaling, no collective), `config4` (one bag of 16384 patches, T=1000, MC
 samples sharded over the ranks + ONE NCCL all-reduce of the Welford partials, with an on-device
-check of the merged statistics against a single-rank run of the same global samples).
+check of the merged statistics against a single-rank run of the same global samples), `config5`
+(N=1 only: image -> tiling -> torch ResNet-18 -> MC head -> attention-map statistics, stage times).
 
 `--impl reference` times the reference's own CPU implementation: `baseline/_ref/model.py` (the
 unmodified reference module, placed there by `__graft_entry__.build()` when `/root/reference`
@@ -502,6 +503,26 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
             iso.append(s0.elapsed_time(s1) * 1e3)
         single["isolated_call_us_median"] = sorted(iso)[len(iso) // 2]
+        # throughput mode: the same single-bag calls round-robin over k private streams, each projection kernel on
+        # 1/k of the SMs, so the fixed per-kernel cost of one call overlaps with the other bags (MCHeadRunner docstring)
+        tp = {}
+        for k in (2, 4):
+            rk = mm.MCHeadRunner(w, 1024, T, n_streams=k)
+            for i in range(40):
+                rk.run(H[(i % nb) * 1024:(i % nb + 1) * 1024], seed=i)
+            rk.synchronize()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for i in range(2 * reps):
+                rk.run(H[(i % nb) * 1024:(i % nb + 1) * 1024], seed=i)
+            t_issue = time.perf_counter() - t0
+            rk.synchronize()
+            dt = time.perf_counter() - t0
+            tp[f"streams_{k}"] = {"us_per_bag": dt / (2 * reps) * 1e6, "bags_per_s": 2 * reps / dt,
+                                  "host_issue_us_per_call": t_issue / (2 * reps) * 1e6,
+                                  "frac_of_burst": f1 / (dt / (2 * reps)) / 1e12 / peak_burst}
+            del rk
+        single["throughput_mode"] = tp
 
     # ---- configs 3 and 4 of BASELINE.json, strong scaling over the ranks of this run
     def config3_leg():
@@ -593,10 +614,57 @@ def run_ours(args):
                                 "per_sample_logits_bit_equal": y_equal,
                                 "bounds": "mean 1e-7 abs, M2 1e-4 of max (fp32 Welford grouping differs), prob mean 1e-6"}}
 
-    config3 = config4 = None
+    def config5_leg():
+        """BASELINE.json configs[4]: the infer.py path end to end on this GPU (infer.py:187-219 without DICOM loading and
+        plotting): synthetic 2294x1914 image -> tiling / bag selection kernels -> torch ResNet-18 (batch-statistics
+        BatchNorm, once per bag) -> fused MC head T=100 -> attention-map statistics per tile-boundary cell."""
+        hh, ww, T5 = 2294, 1914, 100
+        torch.manual_seed(0)
+        model = mm.MultiHeadGatedAttentionMIL(pretrained=False, shared_attention=False)     # config.yml default
+        model.apply(mm.deactivate_batchnorm)                  # infer.py:105-109,154
+        model.to(dev).eval()
+        model.extractor_mode = "channels_last"
+        pt = mm.ImagePatcher(patch_size=224, overlap=0.75, bag_size=-1, empty_thresh=0.75)
+        pt.get_tiles(hh, ww)
+        g5 = torch.Generator(device=dev).manual_seed(0)
+        yy = torch.arange(hh, device=dev).view(-1, 1).float()
+        xx = torch.arange(ww, device=dev).view(1, -1).float()
+        inside = ((yy - hh / 2) / (0.45 * hh)) ** 2 + (xx / (0.8 * ww)) ** 2 < 1.0
+        img = ((torch.rand((1, hh, ww), generator=g5, device=dev) * 0.9 + 0.1) * inside).expand(3, hh, ww).contiguous()
+        times = []
+        for rep in range(4):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
+            bag, idx, _ = pt.convert_img_to_bag(img)
+            ev[1].record()
+            with torch.no_grad():
+                Hf = model.extract_features(bag.unsqueeze(0))
+            ev[2].record()
+            r5 = mm.mc_head(model._head_weights(dev), Hf, T5, seed=rep, return_attention=True)
+            ev[3].record()
+            st = pt.attention_map_stats(r5.A, idx, (hh, ww))
+            mm_, sd_ = st.mean_map(), st.std_map()
+            ev[4].record()
+            torch.cuda.synchronize(dev)
+            if rep > 0:
+                times.append([ev[i].elapsed_time(ev[i + 1]) for i in range(4)])
+        t5 = np.array(times).mean(0)
+        return {"workload": f"{hh}x{ww} synthetic image, overlap 0.75: {len(idx)} of {len(pt.tiles)} tiles, ResNet-18 "
+                            f"(torch, channels-last, batch-statistics BatchNorm), separate attention, T={T5}",
+                "ms": {"tiling_and_bag": float(t5[0]), "resnet18_features_torch": float(t5[1]), "mc_head": float(t5[2]),
+                       "attention_map_stats": float(t5[3]), "total": float(t5.sum())},
+                "images_per_s": 1e3 / float(t5.sum()), "map_shape": list(mm_.shape),
+                "reference_cpu_anchor": "BASELINE.md: tiling 0.67 s, attention-map reconstruction 5.9 s on the survey host"}
+
+    config3 = config4 = config5 = None
     if extras_on and shared and not args.no_configs:
         config3 = config3_leg()
         config4 = config4_leg()
+        if rank == 0 and world == 1:
+            try:
+                config5 = config5_leg()
+            except Exception as e:  # noqa: BLE001   (torchvision missing on the box, ...)
+                config5 = {"error": repr(e)}
 
     # ---- what a reference user with a GPU runs today: the reference's ATen op sequence on this B200 (informational)
     eager = None
@@ -644,7 +712,7 @@ def run_ours(args):
                        "parallelism": "bags sharded over ranks, no collective" if args.workload != "config4"
                        else "MC samples sharded over ranks, one NCCL allreduce of Welford partials"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_f16_features": e2e_f16, "single_bag": single,
-            "separate": separate, "config3": config3, "config4": config4, "torch_cuda_eager": eager,
+            "separate": separate, "config3": config3, "config4": config4, "config5": config5, "torch_cuda_eager": eager,
             "philox_rounds": args.philox_rounds, "philox7_mode": philox7,
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "clocks": clocks, "flops_per_step_per_gpu": flops_step, "hbm_peak_gbs": hbm_peak,

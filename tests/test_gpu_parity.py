@@ -527,6 +527,21 @@ def test_runner_equals_mc_head(mm):
             assert torch.equal(x, y)
     with pytest.raises(ValueError):
         r.run(torch.zeros(10, 512, device=dev))
+    # throughput mode: k private streams, each projection kernel on 1/k of the SMs -> the same bits
+    rk = mm.MCHeadRunner(w, 300, 7, return_attention=True, n_streams=3)
+    Hs = [torch.from_numpy(G.make_features(50 + i, 300)).to(dev) for i in range(7)]
+    outs = []
+    for i, Hi in enumerate(Hs):
+        res = rk.run(Hi, seed=i)
+        if i >= 4:                                     # results stay valid for n_streams further calls
+            res.stream.synchronize()
+            outs.append((i, res.Y.clone(), res.A.clone(), res.attn_m2.clone()))
+    rk.synchronize()
+    for i, Y, A, q in outs:
+        b = mm.mc_head(w, Hs[i], 7, seed=i, return_attention=True)
+        assert torch.equal(Y, b.Y) and torch.equal(A, b.A) and torch.equal(q, b.attn_m2)
+    with pytest.raises(ValueError):
+        mm.MCHeadRunner(w, 300, 7, n_streams=0)
 
 
 def test_extractor_modes_agree(mm):
