@@ -446,18 +446,16 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
 }
 
 int welford_split(int n_cblk, int C, int T) {
-  // Sample groups per (column block, head): the kernel runs 4 CTAs per SM, so a grid just above a multiple of the
-  // 592 CTA slots of a B200 pays a whole extra wave (one bag of 16384 patches at T = 1000: 640 CTAs took two waves,
-  // 51 % of the copy peak).  Pick the split that minimises waves x samples per CTA (plus one unit per group for the
-  // partial write and merge), at least 16 samples per group.
+  // Sample groups per (column block, head).  The kernel runs 4 CTAs per SM (592 CTA slots on a B200): with at least
+  // one full wave of blocks there is nothing to gain (config 2: splitting the 100 samples in two made the kernel 30 %
+  // slower — partial writes, atomics, a second tail); with fewer blocks (one bag, or one large bag) the samples are
+  // split so that the grid fills the slots once, at least 16 samples per group.
   const long long ctas = (long long)n_cblk * C, slots = 4 * 148;
-  long long best = 1, best_cost = -1;
-  for (long long s = 1; s <= COL_MAX_SPLIT && (s == 1 || s <= T / 16); ++s) {
-    const long long waves = (ctas * s + slots - 1) / slots;
-    const long long cost = waves * ((T + s - 1) / s + (s > 1 ? 2 : 0));
-    if (best_cost < 0 || cost < best_cost) { best = s; best_cost = cost; }
-  }
-  return (int)best;
+  if (ctas >= slots) return 1;
+  long long s = slots / ctas;
+  if (s > COL_MAX_SPLIT) s = COL_MAX_SPLIT;
+  if (s > T / 16) s = T / 16;
+  return s < 1 ? 1 : (int)s;
 }
 
 cudaError_t launch_reduce(const Plan& p, const float* logits, const float* scores, uint8_t* workspace,
