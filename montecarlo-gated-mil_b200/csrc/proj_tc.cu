@@ -507,6 +507,10 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       static_assert(!DRAW || (TEAMS == 2 && TEAM_SLICES == 4), "refinement-byte indexing assumes two producer teams");
       uint4 rnd[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};   // primary bytes: [0] row slots 0 (x,y) | 1 (z,w), [1] slots 2 | 3
       uint4 ref = make_uint4(0, 0, 0, 0);                                // word i: row slot i, byte si: this team's si-th slice
+#if defined(MCMIL_PHILOX_BATCH4) && !defined(MCMIL_MASK_HSET2)
+      uint4 q1[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, q2[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      uint4 ref_hold = make_uint4(0, 0, 0, 0);                           // drawn two slices ahead (see the slice loop)
+#endif
 #ifndef MCMIL_MASK_HSET2
       uint32_t fx[4] = {0, 0, 0, 0}, fy[4] = {0, 0, 0, 0};               // [R8 >= T8] flags of the sample's 16 chunks (ref_flags)
 #endif
@@ -591,6 +595,25 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
           }
 #endif
           if constexpr (DRAW) {
+#if defined(MCMIL_PHILOX_BATCH4) && !defined(MCMIL_MASK_HSET2)
+            // Four (five) independent Philox chains every OTHER slice instead of two (three) every slice: with two
+            // chains the LOP3 of a round issues 2-3 slots after the wide multiply it depends on and the warp stalls on
+            // the fixed latency (ncu: `wait` is the top stall reason of the producer warps).  At slice 0: this
+            // sample's slices 1 and 2; at slice 2: slice 3, slice 0 of the next sample and its refinement words.
+            if (si == 0 || si == 2) {
+              const uint32_t qa = q0 + (uint32_t)(TEAMS * (si + 1) * 8);
+              const uint32_t qb = q0 + (uint32_t)(si == 0 ? TEAMS * 2 * 8 : 0);
+              const uint32_t tb = si == 0 ? tg : tg + 1u;
+              q1[0] = philox4x32<ROUNDS>(qa, nrow[0], tg, bag, P.key);
+              q1[1] = philox4x32<ROUNDS>(qa, nrow[2], tg, bag, P.key);
+              q2[0] = philox4x32<ROUNDS>(qb, nrow[0], tb, bag, P.key);
+              q2[1] = philox4x32<ROUNDS>(qb, nrow[2], tb, bag, P.key);
+              if (si == 2) ref_nxt = ref_hold = philox4x32<ROUNDS>(REF_CHUNK_BASE + q0, nrow[0], tb, bag, P.key);
+            }
+            nxt[0] = (si == 0 || si == 2) ? q1[0] : q2[0];
+            nxt[1] = (si == 0 || si == 2) ? q1[1] : q2[1];
+            if (si == TEAM_SLICES - 1) ref_nxt = ref_hold;
+#else
             // next slice of this team: (s + TEAMS, t), or (team, t + 1) after the last one of the sample
             const uint32_t q_next = q0 + (uint32_t)(si < TEAM_SLICES - 1 ? TEAMS * (si + 1) * 8 : 0);
             const uint32_t t_next = si < TEAM_SLICES - 1 ? tg : tg + 1u;
@@ -598,6 +621,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
             nxt[1] = philox4x32<ROUNDS>(q_next, nrow[2], t_next, bag, P.key);
             if (si == TEAM_SLICES - 1)
               ref_nxt = philox4x32<ROUNDS>(REF_CHUNK_BASE + q0, nrow[0], t_next, bag, P.key);
+#endif
           }
           TRACE(tc, 4 * si + 2);
           fence_proxy_async_smem();
