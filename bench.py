@@ -506,7 +506,7 @@ def run_ours(args):
         # throughput mode: the same single-bag calls round-robin over k private streams, each projection kernel on
         # 1/k of the SMs, so the fixed per-kernel cost of one call overlaps with the other bags (MCHeadRunner docstring)
         tp = {}
-        for k in (2, 4):
+        for k in (4, 8):
             rk = mm.MCHeadRunner(w, 1024, T, n_streams=k)
             for i in range(40):
                 rk.run(H[(i % nb) * 1024:(i % nb + 1) * 1024], seed=i)

@@ -507,7 +507,7 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
       static_assert(!DRAW || (TEAMS == 2 && TEAM_SLICES == 4), "refinement-byte indexing assumes two producer teams");
       uint4 rnd[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};   // primary bytes: [0] row slots 0 (x,y) | 1 (z,w), [1] slots 2 | 3
       uint4 ref = make_uint4(0, 0, 0, 0);                                // word i: row slot i, byte si: this team's si-th slice
-#if defined(MCMIL_PHILOX_BATCH4) && !defined(MCMIL_MASK_HSET2)
+#if !defined(MCMIL_PHILOX_BATCH2) && !defined(MCMIL_MASK_HSET2)
       uint4 q1[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, q2[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
       uint4 ref_hold = make_uint4(0, 0, 0, 0);                           // drawn two slices ahead (see the slice loop)
 #endif
@@ -595,11 +595,12 @@ proj_tc_kernel(const __grid_constant__ ProjParams P) {
           }
 #endif
           if constexpr (DRAW) {
-#if defined(MCMIL_PHILOX_BATCH4) && !defined(MCMIL_MASK_HSET2)
+#if !defined(MCMIL_PHILOX_BATCH2) && !defined(MCMIL_MASK_HSET2)
             // Four (five) independent Philox chains every OTHER slice instead of two (three) every slice: with two
             // chains the LOP3 of a round issues 2-3 slots after the wide multiply it depends on and the warp stalls on
             // the fixed latency (ncu: `wait` is the top stall reason of the producer warps).  At slice 0: this
             // sample's slices 1 and 2; at slice 2: slice 3, slice 0 of the next sample and its refinement words.
+            // (Measured 0.5-2 % faster in three A/B pairs, profiles/r2_experiments.md; -DMCMIL_PHILOX_BATCH2: the old order.)
             if (si == 0 || si == 2) {
               const uint32_t qa = q0 + (uint32_t)(TEAMS * (si + 1) * 8);
               const uint32_t qb = q0 + (uint32_t)(si == 0 ? TEAMS * 2 * 8 : 0);
