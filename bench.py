@@ -458,12 +458,15 @@ def run_ours(args):
             dp = torch.empty_like(hp, device=dev)
             for _ in range(2):
                 dp.copy_(hp, non_blocking=True)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(8):
-                dp.copy_(hp, non_blocking=True)
-            torch.cuda.synchronize(dev)
-            e2e["h2d_copy_only_gbs_per_gpu"] = 8 * hp.numel() * 4 / max_over_ranks(time.perf_counter() - t0) / 1e9
+            best = 0.0
+            for _ in range(3):                    # best of 3 x 16 copies of 64 MB, all ranks copying at the same time
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(16):
+                    dp.copy_(hp, non_blocking=True)
+                torch.cuda.synchronize(dev)
+                best = max(best, 16 * hp.numel() * 4 / max_over_ranks(time.perf_counter() - t0) / 1e9)
+            e2e["h2d_copy_only_gbs_per_gpu"] = best
             del hp, dp
 
     # ---- single-bag call latency / back-to-back throughput (the reference's bs == 1 serving loop, infer.py:187-196)

@@ -15,8 +15,9 @@ dev = torch.device("cuda")
 w = mm.HeadWeights(bench.make_state_dict(0, True), dev)
 H = torch.relu(torch.randn(16 * 1024, 512, device=dev))
 calls = 400
-for k in (1, 2, 3, 4, 6, 8):
-    r = mm.MCHeadRunner(w, 1024, 100, n_streams=k)
+import itertools
+for k, reserve in [(1, 0)] + list(itertools.product((4, 6, 8), (0, 8, 16, 28))):
+    r = mm.MCHeadRunner(w, 1024, 100, n_streams=k, reserve_sms=reserve)
     for i in range(40):
         r.run(H[(i % 16) * 1024:(i % 16 + 1) * 1024], seed=i)
     r.synchronize(); torch.cuda.synchronize()
@@ -26,7 +27,7 @@ for k in (1, 2, 3, 4, 6, 8):
     t_issue = time.perf_counter() - t0
     r.synchronize(); torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    print("streams %d: %.2f us per bag (%.0f bags/s), host issue %.2f us per call" % (k, dt / calls * 1e6, calls / dt, t_issue / calls * 1e6), flush=True)
+    print("streams %d reserve %d: %.2f us per bag (%.0f bags/s), host issue %.2f us per call" % (k, reserve, dt / calls * 1e6, calls / dt, t_issue / calls * 1e6), flush=True)
     if k > 1:
         # the same work without the host: every private stream replays a graph of its own calls
         graphs = []
@@ -50,5 +51,5 @@ for k in (1, 2, 3, 4, 6, 8):
                     g.replay()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        print("streams %d: %.2f us per bag replayed from per-stream CUDA graphs" % (k, dt / (5 * 16 * k) * 1e6), flush=True)
+        print("streams %d reserve %d: %.2f us per bag replayed from per-stream CUDA graphs" % (k, reserve, dt / (5 * 16 * k) * 1e6), flush=True)
     del r
