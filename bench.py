@@ -524,7 +524,30 @@ def run_ours(args):
             tp[f"streams_{k}"] = {"us_per_bag": dt / (2 * reps) * 1e6, "bags_per_s": 2 * reps / dt,
                                   "host_issue_us_per_call": t_issue / (2 * reps) * 1e6,
                                   "frac_of_burst": f1 / (dt / (2 * reps)) / 1e12 / peak_burst}
-            del rk
+            # the same calls with no Python in the loop (the host loop above is host bound on slow hosts): every
+            # private stream replays a CUDA graph of 16 of its calls
+            graphs = []
+            for slot in rk.slots:
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(slot.stream):
+                    with torch.cuda.graph(gr, stream=slot.stream):
+                        for i in range(16):
+                            _lib.check(rk.lib.mcmil_head_forward(rk.w._h, slot.plan._h, H[(i % nb) * 1024:].data_ptr(), 0, 0, i,
+                                                                 *slot.tail, slot.stream.cuda_stream), "mcmil_head_forward")
+                graphs.append((gr, slot.stream))
+            for gr, st_ in graphs:
+                with torch.cuda.stream(st_):
+                    gr.replay()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                for gr, st_ in graphs:
+                    with torch.cuda.stream(st_):
+                        gr.replay()
+            torch.cuda.synchronize(dev)
+            dtg = (time.perf_counter() - t0) / (5 * 16 * k)
+            tp[f"streams_{k}"].update({"graph_replay_us_per_bag": dtg * 1e6, "graph_replay_bags_per_s": 1.0 / dtg})
+            del graphs, rk
         single["throughput_mode"] = tp
 
     # ---- configs 3 and 4 of BASELINE.json, strong scaling over the ranks of this run

@@ -304,7 +304,7 @@ class MCHeadRunner:
 
     def __init__(self, weights: HeadWeights, n_rows: int, T: int, p_f: float = 0.1, p_a: float = 0.1,
                  cu_seqlens: Optional[Sequence[int]] = None, return_attention: bool = False,
-                 philox_rounds: int = 10, impl: str = "tcgen05", n_streams: int = 1, reserve_sms: int = 12):
+                 philox_rounds: int = 10, impl: str = "tcgen05", n_streams: int = 1, reserve_sms: int = 0):
         self.lib = _lib.load()
         self.w, self.dev, self.T, self.R = weights, weights.device, int(T), int(n_rows)
         if impl not in _lib.IMPLS:
@@ -322,8 +322,8 @@ class MCHeadRunner:
         if self.n_streams == 1:
             self.slots = [_RunnerSlot(self, cu, 0, None)]
         else:
-            # the projection kernels of the k streams share the SMs; `reserve_sms` stay free for the (small) row /
-            # column kernels of the other bags, which otherwise wait for a projection kernel to end
+            # the projection kernels of the k streams share the SMs; `reserve_sms` of them can be kept free for the
+            # (small) row / column kernels of the other bags (measured: 0 is best, tools/stream_probe.py)
             sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
             share = max(2, ((sms - max(0, int(reserve_sms))) // self.n_streams) & ~1)
             with torch.cuda.device(self.dev):
