@@ -212,12 +212,7 @@ static int head_forward_impl(const mcmil_weights_t* w, const mcmil_plan_t* plan,
   float* scores = reinterpret_cast<float*>(ws + plan->off_score);
   const MaskSpec m = make_mask_spec(t_offset, bag_offset, seed, philox_rounds, p_f, p_a, inj_feat, inj_attn);
   cudaError_t e;
-  // timing experiments only (results are incomplete): MCMIL_EXP_SKIP=proj / reduce drops that stage of the call
-  static const char* exp_skip = getenv("MCMIL_EXP_SKIP");
-  const bool skip_proj = exp_skip && exp_skip[0] == 'p', skip_reduce = exp_skip && exp_skip[0] == 'r';
-  if (skip_proj) {
-    e = cudaSuccess;
-  } else if (impl == MCMIL_IMPL_TCGEN05) {
+  if (impl == MCMIL_IMPL_TCGEN05) {
     if (g_prof.on) {                       // measurement mode: bracket the projection launch(es) with events
       std::lock_guard<std::mutex> lock(g_prof_mu);
       const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
@@ -234,7 +229,6 @@ static int head_forward_impl(const mcmil_weights_t* w, const mcmil_plan_t* plan,
   } else {
     return fail(MCMIL_E_BADARG, "mcmil_head_forward: unknown impl");
   }
-  if (skip_reduce) return 0;
   e = launch_reduce(*plan, logits, scores, ws, Y, A, prob_mean, prob_m2, attn_mean, attn_m2, st, &g_launches);
   if (e != cudaSuccess) return cuda_fail(e, "reduce");
   return 0;
