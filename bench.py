@@ -379,11 +379,11 @@ def run_ours(args):
 
         steps_s = max(3, args.steps // 2)
         ms_s, (ps_ms, ps_k) = timed(sep_step, steps_s, 3, profile=True)
-        fl = sum(flops_per_bag(n, T, C) for n in lens)
-        ks = ps_ms / max(ps_k, 1)                 # per projection launch (one per head)
-        ach = (fl / C) / (ks * 1e-3) / 1e12 if ks > 0 else 0.0
+        fl = sum(flops_per_bag(n, T, C) for n in lens)          # both heads
+        ach = fl * steps_s / (ps_ms * 1e-3) / 1e12 if ps_ms > 0 else 0.0
         separate = {"bags_per_s": n_bags * world * steps_s / (ms_s / 1e3), "ms_per_step": ms_s / steps_s,
-                    "steps": steps_s, "kernel_ms_per_head_launch": ks, "kernel_launches": ps_k,
+                    "steps": steps_s, "projection_ms_per_step": ps_ms / steps_s,
+                    "projection_launches_per_step": ps_k / steps_s,
                     "achieved_tflops": ach, "frac": ach / peak,
                     "flop_rate_vs_shared": (ach / achieved) if achieved > 0 else None}
         del w_sep

@@ -217,8 +217,9 @@ static int head_forward_impl(const mcmil_weights_t* w, const mcmil_plan_t* plan,
       std::lock_guard<std::mutex> lock(g_prof_mu);
       const bool prof = g_prof.on && g_prof.used + 2 <= g_prof.ev.size();
       if (prof) cudaEventRecord(g_prof.ev[g_prof.used], st);
+      const int before = g_launches;
       e = launch_proj_tc(*w, *plan, m, H, h_f16, logits, scores, nullptr, st, &g_launches);
-      if (prof) { cudaEventRecord(g_prof.ev[g_prof.used + 1], st); g_prof.used += 2; g_prof.kernels += w->S; }
+      if (prof) { cudaEventRecord(g_prof.ev[g_prof.used + 1], st); g_prof.used += 2; g_prof.kernels += g_launches - before; }
     } else {
       e = launch_proj_tc(*w, *plan, m, H, h_f16, logits, scores, nullptr, st, &g_launches);
     }
