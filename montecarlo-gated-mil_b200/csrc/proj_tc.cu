@@ -402,15 +402,21 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
 #pragma unroll 1
         for (int s = 0; s < NSLICE; ++s) {
           if (j == 0) mbar_wait(bar_addr(sbase, B_WREADY + s), 0);     // this warp's first sample: W slice s of both CTAs
+#ifndef MCMIL_SEP4_WAIT_CTA
           if constexpr (SEP4) {             // the slice may have been written by another CTA: cluster-scope acquire
             if (!full_ready) mbar_wait_acq_cluster(bar_addr(sbase, B_FULL + q * NSLICE + s), j & 1);
-          } else {
+          } else
+#endif
+          {
             if (!full_ready) WAIT_R(wait_a, bar_addr(sbase, B_FULL + q * NSLICE + s), j & 1, MCMIL_RELAXED_NS_FULL);
           }
           tc_fence_after();
 #ifndef MCMIL_NO_EARLY_PROBE
+#ifndef MCMIL_SEP4_WAIT_CTA
           if constexpr (SEP4) full_ready = s + 1 < NSLICE && mbar_test_wait_acq_cluster(bar_addr(sbase, B_FULL + q * NSLICE + s + 1), j & 1);
-          else full_ready = s + 1 < NSLICE && mbar_test_wait(bar_addr(sbase, B_FULL + q * NSLICE + s + 1), j & 1);
+          else
+#endif
+            full_ready = s + 1 < NSLICE && mbar_test_wait(bar_addr(sbase, B_FULL + q * NSLICE + s + 1), j & 1);
 #endif
           if (elect_one()) {
             // start-address field is (addr >> 4): advancing by bytes/16 stays inside the 14-bit field
@@ -606,11 +612,20 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
                 ref_hold = philox4x32<ROUNDS>(REF_CHUNK_BASE + q0, nrow[0], tg + 1u, bag, P.key);
               }
             }
+#ifdef MCMIL_SEP4_FENCE_CTA
+            fence_proxy_async_smem();
+#else
             fence_proxy_async_all();
+#endif
             __syncwarp();
             if (lane0) {
+#ifdef MCMIL_SEP4_ARRIVE_CTA
+              mbar_arrive_cluster(full_team + (full_set + TEAMS * si) * 8);
+              mbar_arrive_cluster(full_team_sib + (full_set + TEAMS * si) * 8);
+#else
               mbar_arrive_release_cluster(full_team + (full_set + TEAMS * si) * 8);
               mbar_arrive_release_cluster(full_team_sib + (full_set + TEAMS * si) * 8);
+#endif
             }
             if constexpr (DRAW) {
               if (jj == 0) { cur[0] = q1[0]; cur[1] = q1[1]; }
