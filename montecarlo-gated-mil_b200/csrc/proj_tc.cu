@@ -109,7 +109,6 @@ struct ProjParams {
   float sf, hsf, sa;       // 1/(1-p_f), 0.5/(1-p_f), 1/(1-p_a)
   PhiloxKey key;
   EpiConst epi;
-  EpiConst epi1;           // separate attention, both heads in one launch (SEP4): the second head's constants
 };
 
 __device__ __forceinline__ uint32_t bar_addr(uint32_t sbase, uint32_t slot) { return sbase + SM_BAR + slot * 8; }
@@ -194,18 +193,6 @@ __device__ __forceinline__ uint4 keep_masks_int(uint32_t wa, uint32_t wb, uint32
   asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(m.w) : "r"(b));       // features 6, 7
   return m;
 }
-// same as keep_masks_int with the flag word already selected (fx or fy) and the flag in byte 1 (HI = false) or 3
-template <bool HI>
-__device__ __forceinline__ uint4 keep_masks_flag(uint32_t wa, uint32_t wb, uint32_t f, uint32_t neg_d) {
-  const uint32_t cc = __byte_perm(f, 0u, HI ? 0x3333u : 0x1111u);
-  const uint32_t a = (wa | 0x80808080u) + neg_d + cc, b = (wb | 0x80808080u) + neg_d + cc;
-  uint4 m;
-  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(m.x) : "r"(a));
-  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(m.y) : "r"(a));
-  asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(m.z) : "r"(b));
-  asm("prmt.b32 %0, %1, 0, 0xBBAA;" : "=r"(m.w) : "r"(b));
-  return m;
-}
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -216,7 +203,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // 3 + NOUT FMA-type + 4 MUFU instructions per pair instead of 2 x (3 + NOUT) + 4.  acc2[c] holds the
 // (even d, odd d) partial sums of head c.
 template <int HALF, int NOUT, bool DEBUG>
-__device__ __forceinline__ void epilogue_half(const ProjParams& P, const EpiConst& E, uint32_t tbuf, float (&acc)[MAXC],
+__device__ __forceinline__ void epilogue_half(const ProjParams& P, uint32_t tbuf, float (&acc)[MAXC],
                                               float* dbg_row) {
   uint64_t acc2[MAXC];
 #pragma unroll
@@ -248,7 +235,7 @@ __device__ __forceinline__ void epilogue_half(const ProjParams& P, const EpiCons
       for (int i = 0; i < 16; i += 2) {
         const int pr = (64 * part + 32 * HALF + 16 * j + i) >> 1;         // pair of hidden units (d, d+1)
         // one 16-byte constant load: (bv[d], bv[d+1]) | (0.5 bu[d], 0.5 bu[d+1]) as two aligned 64-bit operands
-        const ulonglong2 cb = *reinterpret_cast<const ulonglong2*>(&E.vb[pr]);
+        const ulonglong2 cb = *reinterpret_cast<const ulonglong2*>(&P.epi.vb[pr]);
         const uint64_t xv = fma2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sf2, cb.x);
         const uint64_t xu = fma2(pack2(__uint_as_float(u[i]), __uint_as_float(u[i + 1])), hsf2, cb.y);
         float xv0, xv1, xu0, xu1;
@@ -257,11 +244,11 @@ __device__ __forceinline__ void epilogue_half(const ProjParams& P, const EpiCons
         const uint64_t av = pack2(tanh_approx(xv0), tanh_approx(xv1));
         const uint64_t au = pack2(tanh_approx(xu0), tanh_approx(xu1));
         const uint64_t g2 = fma2(av, au, av);          // 2 * tanh(.) * sigmoid(.)
-        const ulonglong2 h01 = *reinterpret_cast<const ulonglong2*>(&E.hw[pr][0]);
+        const ulonglong2 h01 = *reinterpret_cast<const ulonglong2*>(&P.epi.hw[pr][0]);
         acc2[0] = fma2(g2, h01.x, acc2[0]);
         if constexpr (NOUT > 1) acc2[1] = fma2(g2, h01.y, acc2[1]);
         if constexpr (NOUT > 2) {
-          const ulonglong2 h23 = *reinterpret_cast<const ulonglong2*>(&E.hw[pr][2]);
+          const ulonglong2 h23 = *reinterpret_cast<const ulonglong2*>(&P.epi.hw[pr][2]);
           acc2[2] = fma2(g2, h23.x, acc2[2]);
           if constexpr (NOUT > 3) acc2[3] = fma2(g2, h23.y, acc2[3]);
         }
@@ -276,28 +263,16 @@ __device__ __forceinline__ void epilogue_half(const ProjParams& P, const EpiCons
   }
 }
 
-// SEP4 (separate attention, two heads): one cluster of FOUR CTAs = two CTA pairs, pair p computes head p (its own W
-// set, TMEM, epilogue) on the SAME (tile, sample) units.  The masked A slice of a row half is the same for both heads
-// (model.py:281,297-298: one H_drop feeds every head), so each of the two CTAs that need it draws the masks of HALF of
-// the K-slices (those with (s >> 1) & 1 == p) and writes the masked slice into its own ring and into the sibling
-// CTA's ring (st.shared::cluster): the Philox / mask work per head halves.  Handshake: generic stores ->
-// fence.proxy.async -> mbarrier.arrive.release.cluster on BOTH pair leaders; issue warps wait with acquire.cluster;
-// a ring slot is free again after the commits of BOTH pairs (EMPTY count 2, commit multicast to all four CTAs).
-template <int NOUT, int MASK, bool DEBUG, int ROUNDS, bool SEP4>
-__device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
-  static_assert(!SEP4 || (NOUT == 1 && !DEBUG && RING_EXTRA == 0 && NMMA == 4), "SEP4: one head per pair");
+template <int NOUT, int MASK, bool DEBUG, int ROUNDS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+proj_tc_kernel(const __grid_constant__ ProjParams P) {
   constexpr bool INJECT = MASK == MASK_INJECTED;            // logit masks injected too
   constexpr bool DRAW = MASK == MASK_PHILOX;
-  constexpr int CL = SEP4 ? 4 : 2;                          // CTAs per cluster
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();
-  const uint32_t rank = crank & 1u;                         // position in the CTA pair (which 64-row half)
-  const uint32_t pairi = SEP4 ? crank >> 1 : 0u;            // pair within the cluster = head (SEP4)
-  const uint32_t lead = 2u * pairi;                         // cluster rank of this pair's leader CTA
-  const EpiConst& E = (SEP4 && pairi) ? P.epi1 : P.epi;
-  const int pair = blockIdx.x / CL, n_pairs = gridDim.x / CL;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   long long wait_a = 0, wait_b = 0;          // MCMIL_EXP_WAITSTATS only
   const long long k_t0 = clock64();
 
@@ -309,7 +284,7 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < NMMA * NSLICE; ++s) {
       mbar_init(bar_addr(sbase, B_FULL + s), 2 * TEAM_WARPS);
-      mbar_init(bar_addr(sbase, B_EMPTY + s), SEP4 ? 2 : 1);
+      mbar_init(bar_addr(sbase, B_EMPTY + s), 1);
     }
     for (int b = 0; b < NBUF; ++b) mbar_init(bar_addr(sbase, B_TFULL + b), 1);
     for (int b = 0; b < NMMA; ++b) mbar_init(bar_addr(sbase, B_TEMPTY + b), 8);
@@ -334,7 +309,7 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
     for (int s = 0; s < NSLICE; ++s) {
       const uint32_t wloc = bar_addr(sbase, B_WLOC + s);
       mbar_expect_tx(wloc, SLICE_BYTES_W);
-      bulk_g2s(sbase + SM_W + s * SLICE_BYTES_W, P.wmain + (size_t)((pairi * 2 + rank) * NSLICE + s) * SLICE_BYTES_W, SLICE_BYTES_W, wloc);
+      bulk_g2s(sbase + SM_W + s * SLICE_BYTES_W, P.wmain + (size_t)(rank * NSLICE + s) * SLICE_BYTES_W, SLICE_BYTES_W, wloc);
     }
   }
   cluster_sync();
@@ -361,7 +336,7 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
     if (warp == LOAD_WARP && lane == 0) {
       for (int s = 0; s < NSLICE; ++s) {
         mbar_wait(bar_addr(sbase, B_WLOC + s), 0);
-        mbar_arrive_cluster(mapa(bar_addr(sbase, B_WREADY + s), lead));
+        mbar_arrive_cluster(mapa(bar_addr(sbase, B_WREADY + s), 0));
       }
     }
     __syncwarp();
@@ -402,21 +377,10 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
 #pragma unroll 1
         for (int s = 0; s < NSLICE; ++s) {
           if (j == 0) mbar_wait(bar_addr(sbase, B_WREADY + s), 0);     // this warp's first sample: W slice s of both CTAs
-#ifndef MCMIL_SEP4_WAIT_CTA
-          if constexpr (SEP4) {             // the slice may have been written by another CTA: cluster-scope acquire
-            if (!full_ready) mbar_wait_acq_cluster(bar_addr(sbase, B_FULL + q * NSLICE + s), j & 1);
-          } else
-#endif
-          {
-            if (!full_ready) WAIT_R(wait_a, bar_addr(sbase, B_FULL + q * NSLICE + s), j & 1, MCMIL_RELAXED_NS_FULL);
-          }
+          if (!full_ready) WAIT_R(wait_a, bar_addr(sbase, B_FULL + q * NSLICE + s), j & 1, MCMIL_RELAXED_NS_FULL);
           tc_fence_after();
 #ifndef MCMIL_NO_EARLY_PROBE
-#ifndef MCMIL_SEP4_WAIT_CTA
-          if constexpr (SEP4) full_ready = s + 1 < NSLICE && mbar_test_wait_acq_cluster(bar_addr(sbase, B_FULL + q * NSLICE + s + 1), j & 1);
-          else
-#endif
-            full_ready = s + 1 < NSLICE && mbar_test_wait(bar_addr(sbase, B_FULL + q * NSLICE + s + 1), j & 1);
+          full_ready = s + 1 < NSLICE && mbar_test_wait(bar_addr(sbase, B_FULL + q * NSLICE + s + 1), j & 1);
 #endif
           if (elect_one()) {
             // start-address field is (addr >> 4): advancing by bytes/16 stays inside the 14-bit field
@@ -440,12 +404,12 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
               umma_f16_cg2(db, ad + 2 * kk, bd + ((W_ROWS_A * 128) >> 4) + 2 * kk, IDESC_B, (s | kk) != 0);
             }
 #endif
-            umma_commit_cg2_mc(bar_addr(sbase, B_EMPTY + q * NSLICE + s), SEP4 ? (uint16_t)0xF : (uint16_t)3);
+            umma_commit_cg2_mc(bar_addr(sbase, B_EMPTY + q * NSLICE + s), 3);
           }
           __syncwarp();
           TRACE(NMMA * j + q, 2 + s);
         }
-        if (elect_one()) umma_commit_cg2_mc(bar_addr(sbase, B_TFULL + mbuf), (uint16_t)(3u << lead));
+        if (elect_one()) umma_commit_cg2_mc(bar_addr(sbase, B_TFULL + mbuf), 3);
         __syncwarp();
         mbuf = (mbuf + NMMA) % NBUF;
         mslot = (mslot + NMMA * TEAM_SLICES) % TEAM_SLOTS;
@@ -467,7 +431,7 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
     const int pw = warp - PRODUCER_WARP0;
     const int team = pw >> 2, wt = pw & 3;           // warps of one team sit on the four different schedulers
     // thread-constant addresses, pinned in registers (see ptx::pin)
-    const uint32_t full_team = pin(mapa(bar_addr(sbase, B_FULL), lead) + (uint32_t)team * 8u);    // + (set + TEAMS*si) * 8
+    const uint32_t full_team = pin(mapa(bar_addr(sbase, B_FULL), 0) + (uint32_t)team * 8u);    // + (set + TEAMS*si) * 8
     const uint32_t empty_team = pin(bar_addr(sbase, B_EMPTY) + (uint32_t)team * 8u);
 #ifdef MCMIL_MASK_HSET2
     const uint32_t thr2 = pin(P.thr_f | (P.thr_f << 16));
@@ -484,14 +448,6 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
       rowi[i] = wt * 16 + i * 4 + (lane >> 3);
       off[i] = pin(sbase + SM_RING + (uint32_t)team * SLICE_BYTES_A + (uint32_t)rowi[i] * 128u +
                    (uint32_t)((chunk ^ (rowi[i] & 7)) << 4));             // ring address of slice `team`; + TEAMS*si slices
-    }
-    // SEP4: the same addresses in the sibling CTA (same row half, other head) and its pair leader
-    uint32_t off_r[4] = {0, 0, 0, 0};
-    uint32_t full_team_sib = 0;
-    if constexpr (SEP4) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) off_r[i] = pin(mapa(off[i], crank ^ 2u));
-      full_team_sib = pin(mapa(bar_addr(sbase, B_FULL), lead ^ 2u) + (uint32_t)team * 8u);
     }
     uint32_t tc = 0;                                  // samples processed so far by this pair
     bool slot_free = false;                           // early probe result for the next ring slot
@@ -519,124 +475,6 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
       const int t_end = (int)((u_next < u_end ? u_next : u_end) - (long long)ti * P.T);
       const TileDesc td = u == u_begin ? td_first : P.tiles[ti];
       const uint32_t bag = (uint32_t)(P.bag_offset + td.gbag);
-#ifndef MCMIL_MASK_HSET2
-      if constexpr (SEP4) {
-        // ---- both heads in one launch: this CTA draws the masks of the K-slices s = 2 si + team with si = p, p + 2
-        // (p = its pair index) and writes each masked slice into its own ring AND the sibling CTA's ring.
-        const uint32_t p = pairi;
-        uint4 hreg2[2][4];
-        uint32_t nrow[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int trow = (int)rank * HALF_ROWS + rowi[i];
-          nrow[i] = (uint32_t)(td.n0 + trow);
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const int si = (int)p + 2 * jj;
-            uint4 packed = make_uint4(0, 0, 0, 0);
-            if (trow < td.nrows) {
-              const size_t e0 = (size_t)(td.row0 + trow) * L + (TEAMS * si + team) * KSLICE + chunk * 8;
-              if (P.h_f16) {
-                packed = __ldg(reinterpret_cast<const uint4*>(static_cast<const __half*>(P.H) + e0));
-              } else {
-                const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(P.H) + e0);
-                const float4 a = __ldg(src), b = __ldg(src + 1);
-                packed.x = pack_half2(a.x, a.y); packed.y = pack_half2(a.z, a.w);
-                packed.z = pack_half2(b.x, b.y); packed.w = pack_half2(b.z, b.w);
-              }
-            }
-            hreg2[jj][i] = packed;
-          }
-        }
-        uint4 cur[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, q1[2] = {cur[0], cur[0]}, q2[2] = {cur[0], cur[0]};
-        uint4 ref_hold = make_uint4(0, 0, 0, 0);
-        uint32_t fl[4] = {0, 0, 0, 0};          // [R8 >= T8] flags of this CTA's slices: byte 1 = si = p, byte 3 = si = p + 2
-        auto set_flags = [&](const uint4& r) {
-          const uint32_t sh = p ? 8u : 0u;        // even refinement bytes (si = 0, 2) for p = 0, odd ones (1, 3) for p = 1
-          fl[0] = (((r.x >> sh) & 0x00FF00FFu) | 0x01000100u) - t8x2;
-          fl[1] = (((r.y >> sh) & 0x00FF00FFu) | 0x01000100u) - t8x2;
-          fl[2] = (((r.z >> sh) & 0x00FF00FFu) | 0x01000100u) - t8x2;
-          fl[3] = (((r.w >> sh) & 0x00FF00FFu) | 0x01000100u) - t8x2;
-        };
-        const uint32_t qp = q0 + 16u * p;         // Philox chunk index of slice si = p; + 32 for si = p + 2
-        if constexpr (DRAW) {
-          const uint32_t tg0 = (uint32_t)(P.t_offset + t_begin);
-          set_flags(philox4x32<ROUNDS>(REF_CHUNK_BASE + q0, nrow[0], tg0, bag, P.key));
-          cur[0] = philox4x32<ROUNDS>(qp, nrow[0], tg0, bag, P.key);
-          cur[1] = philox4x32<ROUNDS>(qp, nrow[2], tg0, bag, P.key);
-        }
-#pragma unroll 1
-        for (int t = t_begin; t < t_end; ++t, ++tc) {
-          const uint32_t tg = (uint32_t)(P.t_offset + t);
-          const uint32_t full_set = (tc & (NMMA - 1)) * NSLICE;
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const uint32_t si = p + 2u * (uint32_t)jj;
-            const int s = TEAMS * (int)si + team;
-            // the slot (= K-slice) was last read by the MMAs of sample tc - 1 of BOTH pairs (EMPTY count 2)
-            if (tc != 0u && !slot_free)
-              mbar_wait(empty_team + (((tc - 1u) & (NMMA - 1)) * NSLICE + TEAMS * si) * 8, ((tc - 1u) >> 2) & 1u);
-            const uint32_t slot_off = si * (uint32_t)(TEAMS * SLICE_BYTES_A);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 h = hreg2[jj][i];
-              uint4 m;
-              if constexpr (DRAW) {
-                const uint32_t wa = (i & 1) ? cur[i >> 1].z : cur[i >> 1].x, wb = (i & 1) ? cur[i >> 1].w : cur[i >> 1].y;
-                m = jj == 0 ? keep_masks_flag<false>(wa, wb, fl[i], neg_d) : keep_masks_flag<true>(wa, wb, fl[i], neg_d);
-              } else {
-                const int trow = (int)rank * HALF_ROWS + rowi[i];
-                uint32_t bits = 0;
-                if (trow < td.nrows)
-                  bits = reinterpret_cast<const uint8_t*>(P.inj_feat)[((size_t)t * P.R + td.row0 + trow) * 64 + s * 8 + chunk];
-                m.x = (bits & 1u ? 0x0000FFFFu : 0u) | (bits & 2u ? 0xFFFF0000u : 0u);
-                m.y = (bits & 4u ? 0x0000FFFFu : 0u) | (bits & 8u ? 0xFFFF0000u : 0u);
-                m.z = (bits & 16u ? 0x0000FFFFu : 0u) | (bits & 32u ? 0xFFFF0000u : 0u);
-                m.w = (bits & 64u ? 0x0000FFFFu : 0u) | (bits & 128u ? 0xFFFF0000u : 0u);
-              }
-              const uint4 v = make_uint4(h.x & m.x, h.y & m.y, h.z & m.z, h.w & m.w);
-              sts128(off[i] + slot_off, v);
-              sts128_cluster(off_r[i] + slot_off, v);
-            }
-            {     // probe the EMPTY barrier of the next slot early (see the two-CTA path)
-              const uint32_t tcn = jj == 0 ? tc : tc + 1u, sin = jj == 0 ? p + 2u : p;
-              slot_free = tcn != 0u &&
-                  mbar_test_wait(empty_team + (((tcn - 1u) & (NMMA - 1)) * NSLICE + TEAMS * sin) * 8, ((tcn - 1u) >> 2) & 1u);
-            }
-            if constexpr (DRAW) {
-              if (jj == 0) {       // five independent chains: this sample's second slice, the next sample's first + refinement
-                q1[0] = philox4x32<ROUNDS>(qp + 32u, nrow[0], tg, bag, P.key);
-                q1[1] = philox4x32<ROUNDS>(qp + 32u, nrow[2], tg, bag, P.key);
-                q2[0] = philox4x32<ROUNDS>(qp, nrow[0], tg + 1u, bag, P.key);
-                q2[1] = philox4x32<ROUNDS>(qp, nrow[2], tg + 1u, bag, P.key);
-                ref_hold = philox4x32<ROUNDS>(REF_CHUNK_BASE + q0, nrow[0], tg + 1u, bag, P.key);
-              }
-            }
-#ifdef MCMIL_SEP4_FENCE_CTA
-            fence_proxy_async_smem();
-#else
-            fence_proxy_async_all();
-#endif
-            __syncwarp();
-            if (lane0) {
-#ifdef MCMIL_SEP4_ARRIVE_CTA
-              mbar_arrive_cluster(full_team + (full_set + TEAMS * si) * 8);
-              mbar_arrive_cluster(full_team_sib + (full_set + TEAMS * si) * 8);
-#else
-              mbar_arrive_release_cluster(full_team + (full_set + TEAMS * si) * 8);
-              mbar_arrive_release_cluster(full_team_sib + (full_set + TEAMS * si) * 8);
-#endif
-            }
-            if constexpr (DRAW) {
-              if (jj == 0) { cur[0] = q1[0]; cur[1] = q1[1]; }
-              else { cur[0] = q2[0]; cur[1] = q2[1]; set_flags(ref_hold); }
-            }
-          }
-        }
-        u = u_next < u_end ? u_next : u_end;
-        continue;
-      }
-#endif
       // this thread's 16 chunks (4 slices of its team x 4 row slots) of the fp16 feature tile: registers
       uint4 hreg[TEAM_SLICES][4];
       uint32_t nrow[4];
@@ -812,7 +650,7 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
     const int half = warp >> 1;                    // TMEM lanes 64..127: the peer CTA's W rows
     const int r = (warp & 1) * 32 + lane;          // patch row within this CTA's 64-row half tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const uint32_t tempty_leader = mapa(bar_addr(sbase, B_TEMPTY), lead);
+    const uint32_t tempty_leader = mapa(bar_addr(sbase, B_TEMPTY), 0);
     float* xch = reinterpret_cast<float*>(smem + SM_XCH);
     uint32_t tc = 0, buf = 0, buf_phase = 0;      // accumulator buffer tc % NBUF and the parity of its use count
     TRACE_DECL
@@ -842,8 +680,8 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
           if (P.dbg != nullptr && tc == 0)
             dbg_row = P.dbg + ((size_t)(pair * 2 + (int)rank) * 128 + warp * 32 + lane) * 136;
         }
-        if (half == 0) epilogue_half<0, NOUT, DEBUG>(P, E, lane_base + buf * TM_BUF_STRIDE, acc, dbg_row);
-        else           epilogue_half<1, NOUT, DEBUG>(P, E, lane_base + buf * TM_BUF_STRIDE, acc, dbg_row);
+        if (half == 0) epilogue_half<0, NOUT, DEBUG>(P, lane_base + buf * TM_BUF_STRIDE, acc, dbg_row);
+        else           epilogue_half<1, NOUT, DEBUG>(P, lane_base + buf * TM_BUF_STRIDE, acc, dbg_row);
         uint32_t sc[8];
         tmem_ld8(lane_base + buf * TM_BUF_STRIDE + TM_A + 64, sc);
         tmem_ld_wait();
@@ -872,7 +710,7 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
             rnd = attn_words<ROUNDS>(0u, (uint32_t)(td.n0 + trow), tg, (uint32_t)(P.bag_offset + td.gbag), P.key);
 #pragma unroll
           for (int c = 0; c < NOUT; ++c) {
-            const int head = P.head0 + c + (int)pairi;
+            const int head = P.head0 + c;
             bool keep;
             if constexpr (!INJECT) keep = attn_keep_from(rnd, head, P.thr_a);
             else keep = (P.inj_attn[((size_t)t * P.C + head) * P.Rw + (g >> 5)] >> (g & 31)) & 1u;
@@ -893,8 +731,8 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
           }
 #pragma unroll
           for (int c = 0; c < NOUT; ++c) {
-            const int head = P.head0 + c + (int)pairi;
-            const float logit = acc[c] + part[c] + E.bw[c];
+            const int head = P.head0 + c;
+            const float logit = acc[c] + part[c] + P.epi.bw[c];
             const size_t o = ((size_t)t * P.C + head) * P.Rp + td.pcol0 + trow;
             P.logits[o] = mult[c] != 0.f ? logit * mult[c] : 0.f;   // a dropped logit is 0, not -inf (model.py:291,305)
             P.scores[o] = (__uint_as_float(sc[c]) + __uint_as_float(sc[4 + c])) * P.sf;
@@ -922,18 +760,6 @@ __device__ __forceinline__ void proj_tc_body(const ProjParams& P) {
   }
 }
 
-template <int NOUT, int MASK, bool DEBUG, int ROUNDS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-proj_tc_kernel(const __grid_constant__ ProjParams P) {
-  proj_tc_body<NOUT, MASK, DEBUG, ROUNDS, false>(P);
-}
-// separate attention with two heads: both heads in one launch (see proj_tc_body)
-template <int MASK, int ROUNDS>
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(TC_THREADS, 1)
-proj_tc_sep4_kernel(const __grid_constant__ ProjParams P) {
-  proj_tc_body<1, MASK, false, ROUNDS, true>(P);
-}
-
 cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, const void* H, int h_f16,
                            float* logits, float* scores, float* dbg, cudaStream_t st, int* launches) {
   using KernelFn = void (*)(ProjParams);
@@ -948,10 +774,6 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
        {proj_tc_kernel<1, MASK_INJECTED, false, 10>, proj_tc_kernel<2, MASK_INJECTED, false, 10>,
         proj_tc_kernel<3, MASK_INJECTED, false, 10>, proj_tc_kernel<4, MASK_INJECTED, false, 10>}}};
   static const KernelFn debug_kernel = proj_tc_kernel<2, MASK_PHILOX, true, 10>;   // raw-accumulator dump (tests only)
-  // separate attention with two heads, both in one launch: [rounds 10 / 7][mask source]
-  static const KernelFn sep4_kernels[2][2] = {
-      {proj_tc_sep4_kernel<MASK_PHILOX, 10>, proj_tc_sep4_kernel<MASK_INJECTED, 10>},
-      {proj_tc_sep4_kernel<MASK_PHILOX, 7>, proj_tc_sep4_kernel<MASK_INJECTED, 10>}};
   if (dbg != nullptr && !(w.shared && w.C == 2 && m.inj_feat == nullptr && m.rounds == 10)) return cudaErrorInvalidValue;
   // The dynamic shared memory opt-in is a PER-DEVICE function attribute and the SM count a per-device property:
   // both are set / queried once per device ordinal, under a mutex (several host threads may drive several GPUs).
@@ -973,11 +795,6 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
           }
       cudaError_t e = cudaFuncSetAttribute(debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
       if (e != cudaSuccess) return e;
-      for (int r = 0; r < 2; ++r)
-        for (int a = 0; a < 2; ++a) {
-          e = cudaFuncSetAttribute(sep4_kernels[r][a], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
-          if (e != cudaSuccess) return e;
-        }
       e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (e != cudaSuccess) return e;
       if (dev >= 0 && dev < 64) sms_of[dev] = sms;
@@ -990,36 +807,6 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
   if (p.sm_limit > 0 && p.sm_limit / 2 < n_pairs) n_pairs = p.sm_limit / 2 > 0 ? p.sm_limit / 2 : 1;
   if (units < n_pairs) n_pairs = (int)units;
   if (n_pairs < 1) return cudaSuccess;
-  const int mask_mode_all = m.inj_feat != nullptr ? MASK_INJECTED : MASK_PHILOX;
-#ifndef MCMIL_MASK_HSET2
-  // Separate attention with two heads (the reference's config.yml default): ONE launch, clusters of four CTAs, the
-  // masks of a sample drawn once for both heads (proj_tc_body, SEP4).  MCMIL_NO_SEP4=1: one launch per head.
-  static const bool no_sep4 = getenv("MCMIL_NO_SEP4") != nullptr;
-  if (!w.shared && w.C == 2 && dbg == nullptr && !no_sep4 && sms >= 4) {
-    int n_cl = sms / 4;
-    if (p.sm_limit > 0 && p.sm_limit / 4 < n_cl) n_cl = p.sm_limit / 4 > 0 ? p.sm_limit / 4 : 1;
-    if (units < n_cl) n_cl = (int)units;
-    ProjParams P;
-    P.H = H; P.h_f16 = h_f16;
-    P.wmain = w.d_wmain;                      // set 0 | set 1, each [2 ranks][8 slices]
-    P.tiles = p.d_tiles;
-    P.logits = logits; P.scores = scores;
-    P.inj_feat = m.inj_feat; P.inj_attn = m.inj_attn;
-    P.dbg = nullptr;
-    P.n_tiles = p.n_tiles; P.T = p.T; P.C = p.C; P.R = p.R; P.Rp = p.Rp; P.Rw = p.Rw;
-    P.n_out = 1; P.head0 = 0;                 // pair p of a cluster writes head p
-    P.t_offset = m.t_offset; P.bag_offset = m.bag_offset;
-    P.thr_f = m.thr_f; P.thr_a = m.thr_a;
-    P.sf = m.sf; P.hsf = 0.5f * m.sf; P.sa = m.sa;
-    P.key = m.key;
-    P.epi = w.epi[0]; P.epi1 = w.epi[1];
-    PdlLaunch L(dim3(4 * n_cl), dim3(TC_THREADS), SM_TOTAL, st);
-    cudaError_t e = cudaLaunchKernelEx(&L.cfg, sep4_kernels[m.rounds == 7 ? 1 : 0][mask_mode_all], P);
-    if (e != cudaSuccess) return e;
-    if (launches) ++*launches;
-    return cudaGetLastError();
-  }
-#endif
   for (int s = 0; s < w.S; ++s) {
     ProjParams P;
     P.H = H; P.h_f16 = h_f16;
@@ -1035,8 +822,8 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
     P.thr_f = m.thr_f; P.thr_a = m.thr_a;
     P.sf = m.sf; P.hsf = 0.5f * m.sf; P.sa = m.sa;
     P.key = m.key;
-    P.epi = w.epi[s]; P.epi1 = w.epi[s];
-    // separate attention with 1, 3 or 4 heads: every head's launch redraws the same Philox masks (the same H_drop feeds all heads,
+    P.epi = w.epi[s];
+    // separate attention: every head's launch redraws the same Philox masks (the same H_drop feeds all heads,
     // model.py:281,297-298); a keep-bit cache in HBM was measured no faster once a call costs 1/16 per element
     const int mask_mode = m.inj_feat != nullptr ? MASK_INJECTED : MASK_PHILOX;
     const KernelFn fn = dbg != nullptr ? debug_kernel : kernels[m.rounds == 7 ? 1 : 0][mask_mode][P.n_out - 1];

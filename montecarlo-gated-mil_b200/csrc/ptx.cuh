@@ -82,38 +82,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #endif
 }
 
-// cluster-scope variants for data another CTA wrote into this CTA's shared memory with generic stores
-// (st.shared::cluster): the writer arrives with release.cluster, the reader waits with acquire.cluster
-__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_test_wait_acq_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\t"
-               "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-               "selp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_acq_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
-                 "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)MCMIL_WAIT_HINT_NS) : "memory");
-    if (ok) return;
-#ifndef MCMIL_UNBOUNDED_WAITS
-    if (++spins > (1u << 20)) { __trap(); }
-#endif
-  }
-}
-// st.shared::cluster.v4 at a shared::cluster address (mapa): a 16-byte store into another CTA's shared memory
-__device__ __forceinline__ void sts128_cluster(uint32_t cluster_addr, const uint4& v) {
-  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
 // st.shared.v4 at a 32-bit shared address
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -124,8 +92,6 @@ __device__ __forceinline__ uint32_t pin(uint32_t v) { asm volatile("mov.u32 %0, 
 
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// all state spaces (own and remote shared memory written through the generic proxy)
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
