@@ -192,3 +192,24 @@ def test_patcher_grid_must_fit_the_image_and_follows_tiles_assignment():
     src = pt._tiles_src
     pt.tiles = pt.tiles.copy()               # the reference's dataset assigns patcher.tiles directly
     assert pt._tiles_src is src and pt._tiles_src is not pt.tiles   # stale until the next use refreshes it
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (what the driver runs next to our arm): one JSON line with the contract's keys,
+    the CPU arm described in `cpu_baseline`, `e2e` repeating the line's own value with zero copies."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in rec, key
+    assert rec["impl"] == "reference" and rec["unit"] == "bags/s" and rec["higher_is_better"] is True
+    assert rec["cpu_baseline"]["kind"] in ("reference", "port") and rec["cpu_baseline"]["cores"] >= 1
+    assert rec["e2e"]["value"] == rec["value"] and rec["e2e"]["h2d_bytes_per_step"] == 0
