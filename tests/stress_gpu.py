@@ -41,3 +41,34 @@ for it in range(iters):
     if not ok:
         sys.exit(1)
 print("stress ok, worst relative attention difference", worst)
+
+# ---- reductions across their dispatch regimes (warp / chunked-warp / CTA row kernels; column kernel with 1..16 sample
+# groups, partial tiles, many bags): the statistics must be the statistics of the returned samples, every softmax row
+# sums to one, Y equals the pooled scores recomputed from A by the fp32 path
+shapes = [([1024] * 40, 60), ([3000, 200, 1500] * 12, 50), ([16384], 200), ([5000, 70], 33), ([1] * 300, 16), ([129] * 9, 1000),
+          ([2049, 4097], 17), ([33] * 70, 2)]
+for lens, T in shapes:
+    C = int(rng.integers(1, 5))
+    sd = G.make_weights(int(rng.integers(0, 1000)), C, bool(rng.integers(0, 2)))
+    w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
+    cu = np.concatenate([[0], np.cumsum(lens)])
+    g = torch.Generator(device=dev).manual_seed(int(rng.integers(0, 1 << 30)))
+    H = torch.relu(torch.randn(int(cu[-1]), 512, generator=g, device=dev))
+    r = mm.mc_head(w, H, T, seed=int(rng.integers(0, 1 << 30)), cu_seqlens=cu, return_attention=True)
+    A = r.A.double()
+    seg = torch.from_numpy(np.repeat(np.arange(len(lens)), lens)).to(dev)
+    row_sums = torch.zeros(T, C, len(lens), dtype=torch.float64, device=dev).index_add_(2, seg, A)
+    e_sum = float((row_sums - 1).abs().max())
+    e_mean = float((A.mean(0) - r.attn_mean.double()).abs().max() / A.mean(0).abs().max())
+    m2 = ((A - A.mean(0)) ** 2).sum(0)
+    e_m2 = float((m2 - r.attn_m2.double()).abs().max() / m2.abs().max().clamp_min(1e-300)) if T > 1 else 0.0
+    P = torch.softmax(r.Y.double(), -1)
+    e_pm = float((P.mean(1) - r.prob_mean.double()).abs().max())
+    e_pq = float((((P - P.mean(1, keepdim=True)) ** 2).sum(1) - r.prob_m2.double()).abs().max())
+    ok = e_sum < 2e-5 and e_mean < 2e-6 and e_m2 < 2e-4 and e_pm < 1e-6 and e_pq < 1e-5 and bool(torch.isfinite(r.Y).all())
+    print(f"reduce n_bags={len(lens)} max_n={max(lens)} T={T} C={C}: rowsum {e_sum:.1e} mean {e_mean:.1e} m2 {e_m2:.1e} "
+          f"pmean {e_pm:.1e} pm2 {e_pq:.1e} {'ok' if ok else 'FAIL'}", flush=True)
+    if not ok:
+        sys.exit(1)
+    del r, A
+print("reduction stress ok")
