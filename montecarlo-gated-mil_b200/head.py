@@ -283,6 +283,7 @@ class _RunnerSlot:
                      _ptr(self.Y), _ptr(self.A), _ptr(self.pm), _ptr(self.pq), _ptr(self.am), _ptr(self.aq),
                      C.c_void_p(self.ws.data_ptr() + off), self.plan.ws_bytes)
         self.stream = stream
+        self.stream_handle = stream.cuda_stream if stream is not None else None
         self.result = MCHeadResult(self.Y, self.pm, self.pq, self.am, self.aq, self.A, T, cu, 0)
         self.result.stream = stream
 
@@ -332,7 +333,10 @@ class MCHeadRunner:
         self.plan = self.slots[0].plan
         self.result = self.slots[0].result
 
-    def run(self, H: torch.Tensor, seed: int = 0, t_offset: int = 0, bag_offset: int = 0) -> MCHeadResult:
+    def run(self, H: torch.Tensor, seed: int = 0, t_offset: int = 0, bag_offset: int = 0,
+            sync_input: bool = True) -> MCHeadResult:
+        """sync_input (throughput mode only): make the private stream wait for the caller's current stream, on which H
+        was produced (one event record + wait, ~3 us of host time); pass False when H is known to be ready."""
         if H.device != self.dev or H.dtype != torch.float32 or tuple(H.shape) != (self.R, L_FEAT) or not H.is_contiguous():
             raise ValueError(f"MCHeadRunner.run: H must be a contiguous float32 ({self.R}, {L_FEAT}) tensor on {self.dev}")
         slot = self.slots[self._next]
@@ -340,11 +344,11 @@ class MCHeadRunner:
             stream = torch.cuda.current_stream(self.dev).cuda_stream
         else:
             self._next = (self._next + 1) % self.n_streams
-            slot.stream.wait_stream(torch.cuda.current_stream(self.dev))       # H was produced on the caller's stream
-            stream = slot.stream.cuda_stream
-        code = self.lib.mcmil_head_forward(self.w._h, slot.plan._h, C.c_void_p(H.data_ptr()), int(t_offset),
-                                           int(bag_offset), int(seed) & 0xFFFFFFFFFFFFFFFF, *slot.tail,
-                                           C.c_void_p(stream))
+            if sync_input:
+                slot.stream.wait_stream(torch.cuda.current_stream(self.dev))   # H was produced on the caller's stream
+            stream = slot.stream_handle
+        code = self.lib.mcmil_head_forward(self.w._h, slot.plan._h, H.data_ptr(), int(t_offset),
+                                           int(bag_offset), int(seed) & 0xFFFFFFFFFFFFFFFF, *slot.tail, stream)
         if code:
             _lib.check(code, "mcmil_head_forward")
         return slot.result
