@@ -192,6 +192,18 @@ def cpu_head_bags_per_s(n_bags, N, T, shared, threads, warmup=1):
     return n_bags / sum(times), times, head
 
 
+def config_of(name, n_bags, rows_per_gpu, T, C, shared, strong):
+    """The `config` object of the JSON line: both arms print the same one (the reference arm measures the same
+    metric on a bounded sample of this workload)."""
+    return {"workload": f"{name}: {n_bags} bag(s){'' if strong else ' per GPU'} per step, "
+                        f"N={'1024' if name == 'config2' else 'var'} patches x 512 features, T={T} MC passes, {C} heads, "
+                        f"{'shared' if shared else 'separate'} attention, p_f=p_a=0.1",
+            "bags_per_step_per_gpu": n_bags, "rows_per_step_per_gpu": rows_per_gpu,
+            "l2_policy": "inputs larger than L2 (%.0f MB of features per step per GPU), no flush" % (rows_per_gpu * L * 4 / 1e6),
+            "parallelism": "bags sharded over ranks, no collective" if name != "config4"
+            else "MC samples sharded over ranks, one NCCL allreduce of Welford partials"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -199,6 +211,11 @@ def run_reference(args):
     lens, T = workload(args.workload, 1, args.seed)
     N = lens[0]
     cores = os.cpu_count() or 1
+    # the line carries OUR arm's config (same metric on the same workload); what one step of this arm runs is a
+    # bounded sample of it, described in cpu_baseline.sample
+    all_lens, _ = workload(args.workload, args.bags_per_step, args.seed)
+    strong = args.workload in ("config3", "config4") and args.gpus > 1
+    ours_config = config_of(args.workload, len(all_lens), sum(all_lens), T, 2, not args.separate, strong)
     T_run = T if args.workload != "config4" else 25     # the reference cannot materialise (1000,1,16384,512)
     t0 = time.perf_counter()
     bps, times, head = cpu_head_bags_per_s(args.steps, N, T_run, not args.separate, cores, warmup=args.warmup)
@@ -210,8 +227,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": bps, "unit": "bags/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: N={N} patches x 512, T={T}, 2 heads, "
-                               f"{'separate' if args.separate else 'shared'} attention; 1 bag per step on host cores"},
+        "config": ours_config,
         "cpu_baseline": {"value": bps, "unit": "bags/s", "cores": cores, "kind": head.kind, "sample": sample},
         "e2e": {"value": bps, "unit": "bags/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
@@ -729,14 +745,8 @@ def run_ours(args):
             "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f16xf16->f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {len(all_lens) if strong else n_bags} bag(s)"
-                                   f"{'' if strong else ' per GPU'} per step, N={'1024' if args.workload == 'config2' else 'var'} "
-                                   f"patches x 512 features, T={merged_T[0] if strong else T} MC passes, {C} heads, "
-                                   f"{'shared' if shared else 'separate'} attention, p_f=p_a=0.1, in-kernel Philox masks",
-                       "bags_per_step_per_gpu": n_bags, "rows_per_step_per_gpu": R,
-                       "l2_policy": "inputs larger than L2 (%.0f MB of features per step per GPU), no flush" % (R * L * 4 / 1e6),
-                       "parallelism": "bags sharded over ranks, no collective" if args.workload != "config4"
-                       else "MC samples sharded over ranks, one NCCL allreduce of Welford partials"},
+            "config": config_of(args.workload, len(all_lens) if strong else n_bags, R, merged_T[0] if strong else T,
+                                C, shared, strong),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_f16_features": e2e_f16, "single_bag": single,
             "separate": separate, "config3": config3, "config4": config4, "config5": config5, "torch_cuda_eager": eager,
             "philox_rounds": args.philox_rounds, "philox7_mode": philox7,
