@@ -99,25 +99,38 @@ __device__ __forceinline__ void prob_stats_warp(const float* y, int T, int C, in
 
 // ================================================================================== generic path, launch 1: rows
 constexpr int ROW_THREADS = 256;
+constexpr int ROW_WARPS = ROW_THREADS / 32;
 
-// One WARP per (bag, t, c) row, eight rows per CTA, any row length: the row is walked in chunks of 1024 patches
-// (8 float4 per lane and plane, all 16 loads of a chunk issued before the first use); max and exp / sum of a chunk run
-// on the registers, chunks are merged with the running (max, sum) on the fly, so each plane is read from DRAM exactly
-// once.  Two CTAs per SM (98 registers) keep the loads of other warps in flight while one warp reduces.  Block 0 also
-// clears the arrival counters of the column kernel.
+// WPR warps per (bag, t, c) row, ROW_WARPS / WPR rows per CTA, any row length.  A warp walks its share of the row in
+// chunks of 128 * V4 patches (V4 float4 per lane and plane, all 2 * V4 loads of a chunk issued before the first use);
+// max and exp / sum of a chunk run on the registers and chunks are merged with the warp's running (max, sum, pooled
+// score) on the fly, so each plane is read from DRAM exactly once and no warp ever waits for another one before the
+// end of the row.
+//   WPR = 1 (many rows: >= 2048): a warp owns a row.  LOOP = false: every row fits one chunk (no loop-carried
+//     state: 80 registers, 3 CTAs per SM); LOOP = true: 98 registers, 2 CTAs per SM.
+//   WPR = 8 (few rows: one bag, or long rows): the CTA's warps take the row's chunks round-robin and their running
+//     statistics are merged through shared memory once, after one __syncthreads.  V4 is chosen by the launcher so
+//     that a row of up to 8 * 128 * V4 patches is one chunk per warp.  (Round 1/2 kept a whole 16384-patch chunk in
+//     the registers of one CTA: 157 registers, ONE CTA per SM, two block-wide reductions per row — 75 % of the copy
+//     peak at config 4, and 64 exp of -inf per thread on the 1024-patch rows of a single-bag call.)
+// Block 0 also clears the arrival counters of the column kernel.
 constexpr int ROWW_V4 = 8;
-template <bool LOOP>          // false: every row fits one chunk (no loop-carried state: 80 registers, 3 CTAs per SM)
-__global__ void __launch_bounds__(ROW_THREADS, LOOP ? 2 : 3)
+template <bool LOOP, int WPR, int V4>
+__global__ void __launch_bounds__(ROW_THREADS, (LOOP && V4 == 8) ? 2 : 3)
 softmax_rows_warp_kernel(const float* __restrict__ logits, const float* __restrict__ scores,
                          const int32_t* __restrict__ cu, const int32_t* __restrict__ pcol, int n_bags, int T, int C,
                          int Rp, float2* __restrict__ rowstat, float* __restrict__ Y, int* __restrict__ wcount,
                          int n_wcount) {
+  static_assert(WPR == 1 || WPR == ROW_WARPS, "a warp or the whole CTA per row");
+  static_assert(LOOP || WPR == 1, "the one-chunk form is for warp-per-row launches");
+  __shared__ float red[3][ROW_WARPS];
   grid_dep_sync();
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < n_wcount; i += ROW_THREADS) wcount[i] = 0;
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5);
-  if (row >= (long long)n_bags * T * C) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = WPR == 1 ? 0 : warp;                        // this warp's position among the row's warps
+  const long long row = WPR == 1 ? (long long)blockIdx.x * ROW_WARPS + warp : (long long)blockIdx.x;
+  if (row >= (long long)n_bags * T * C) return;               // (WPR = 8: uniform over the CTA)
   const int c = (int)(row % C);
   const int t = (int)((row / C) % T);
   const int b = (int)(row / ((long long)C * T));
@@ -125,18 +138,18 @@ softmax_rows_warp_kernel(const float* __restrict__ logits, const float* __restri
   const size_t off = ((size_t)t * C + c) * Rp + pcol[b];
   const float4* lg = reinterpret_cast<const float4*>(logits + off);
   const float4* sc = reinterpret_cast<const float4*>(scores + off);
-  float M = -INFINITY, Z = 0.f, Yv = 0.f;                     // running row statistics (warp-uniform)
-  for (int base = 0; base < (LOOP ? n : 1); base += 128 * ROWW_V4) {
-    float4 v[ROWW_V4], w[ROWW_V4];
+  float M = -INFINITY, Z = 0.f, Yv = 0.f;                     // running statistics of this warp's chunks (warp-uniform)
+  for (int base = sub * 128 * V4; base < (LOOP ? n : 1); base += WPR * 128 * V4) {
+    float4 v[V4], w[V4];
 #pragma unroll
-    for (int k = 0; k < ROWW_V4; ++k) {
+    for (int k = 0; k < V4; ++k) {
       const int i4 = base / 4 + lane + 32 * k;
       if (4 * i4 < n) { v[k] = __ldg(lg + i4); w[k] = __ldg(sc + i4); }
       else { v[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); w[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
     }
     float m = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < ROWW_V4; ++k) {
+    for (int k = 0; k < V4; ++k) {
       const int col = base + 4 * (lane + 32 * k);             // the bag's last float4 may reach into the plane padding
       if (col + 1 >= n) { v[k].y = -INFINITY; w[k].y = 0.f; }
       if (col + 2 >= n) { v[k].z = -INFINITY; w[k].z = 0.f; }
@@ -146,7 +159,7 @@ softmax_rows_warp_kernel(const float* __restrict__ logits, const float* __restri
     m = warp_max(m);
     float z = 0.f, y = 0.f;
 #pragma unroll
-    for (int k = 0; k < ROWW_V4; ++k) {
+    for (int k = 0; k < V4; ++k) {
       const float e0 = fast_exp(v[k].x - m), e1 = fast_exp(v[k].y - m);      // exp(-inf) = 0 for the padding
       const float e2 = fast_exp(v[k].z - m), e3 = fast_exp(v[k].w - m);
       z += (e0 + e1) + (e2 + e3);
@@ -159,84 +172,26 @@ softmax_rows_warp_kernel(const float* __restrict__ logits, const float* __restri
     Yv = fmaf(Yv, fa, y * fb);
     M = Mn;
   }
+  if constexpr (WPR > 1) {
+    // merge the warps' statistics in warp order (a warp without a chunk holds (-inf, 0, 0) and drops out)
+    if (lane == 0) { red[0][warp] = M; red[1][warp] = Z; red[2][warp] = Yv; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    M = red[0][0]; Z = red[1][0]; Yv = red[2][0];
+#pragma unroll
+    for (int q = 1; q < ROW_WARPS; ++q) {
+      const float m = red[0][q];
+      if (m == -INFINITY) continue;
+      const float Mn = fmaxf(M, m);
+      const float fa = fast_exp(M - Mn), fb = fast_exp(m - Mn);
+      Z = fmaf(Z, fa, red[1][q] * fb);
+      Yv = fmaf(Yv, fa, red[2][q] * fb);
+      M = Mn;
+    }
+  }
   if (lane == 0) {
     const float inv = 1.0f / Z;
     rowstat[((size_t)c * n_bags + b) * T + t] = make_float2(M, inv);   // [C][n_bags][T]: a row's samples are contiguous
-    Y[((size_t)b * T + t) * C + c] = Yv * inv;
-  }
-}
-
-// Long rows: one CTA per (bag, t, c) row.  A chunk of up to 16384 patches of both planes lives in registers
-// (16 float4 per thread and plane, all loads issued before the first use), so a row of that length is read from
-// DRAM exactly once; longer rows take several chunks, merged with the running (max, sum) on the fly.
-constexpr int ROWC_V4 = 16;
-__global__ void __launch_bounds__(ROW_THREADS)
-softmax_rows_cta_kernel(const float* __restrict__ logits, const float* __restrict__ scores,
-                        const int32_t* __restrict__ cu, const int32_t* __restrict__ pcol, int n_bags, int T, int C,
-                        int Rp, float2* __restrict__ rowstat, float* __restrict__ Y, int* __restrict__ wcount,
-                        int n_wcount) {
-  __shared__ float red[3][ROW_THREADS / 32];
-  grid_dep_sync();
-  if (blockIdx.x == 0)
-    for (int i = threadIdx.x; i < n_wcount; i += ROW_THREADS) wcount[i] = 0;
-  const int c = blockIdx.x % C;
-  const int t = (blockIdx.x / C) % T;
-  const int b = blockIdx.x / (C * T);
-  const int n = cu[b + 1] - cu[b];
-  const size_t off = ((size_t)t * C + c) * Rp + pcol[b];
-  const float4* lg = reinterpret_cast<const float4*>(logits + off);
-  const float4* sc = reinterpret_cast<const float4*>(scores + off);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float M = -INFINITY, Z = 0.f, Yv = 0.f;                     // running row statistics (meaningful in thread 0)
-  for (int base = 0; base < n; base += 4 * ROW_THREADS * ROWC_V4) {
-    float4 v[ROWC_V4], w[ROWC_V4];
-#pragma unroll
-    for (int k = 0; k < ROWC_V4; ++k) {
-      const int i4 = base / 4 + threadIdx.x + ROW_THREADS * k;
-      if (4 * i4 < n) { v[k] = __ldg(lg + i4); w[k] = __ldg(sc + i4); }
-      else { v[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); w[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
-    }
-    float m = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < ROWC_V4; ++k) {
-      const int col = base + 4 * (threadIdx.x + ROW_THREADS * k);
-      if (col + 1 >= n) { v[k].y = -INFINITY; w[k].y = 0.f; }
-      if (col + 2 >= n) { v[k].z = -INFINITY; w[k].z = 0.f; }
-      if (col + 3 >= n) { v[k].w = -INFINITY; w[k].w = 0.f; }
-      m = fmaxf(fmaxf(m, fmaxf(v[k].x, v[k].y)), fmaxf(v[k].z, v[k].w));
-    }
-    m = warp_max(m);
-    if (lane == 0) red[0][warp] = m;
-    __syncthreads();
-    m = red[0][0];
-#pragma unroll
-    for (int q = 1; q < ROW_THREADS / 32; ++q) m = fmaxf(m, red[0][q]);
-    float z = 0.f, y = 0.f;
-#pragma unroll
-    for (int k = 0; k < ROWC_V4; ++k) {
-      const float e0 = fast_exp(v[k].x - m), e1 = fast_exp(v[k].y - m);
-      const float e2 = fast_exp(v[k].z - m), e3 = fast_exp(v[k].w - m);
-      z += (e0 + e1) + (e2 + e3);
-      y = fmaf(e0, w[k].x, y); y = fmaf(e1, w[k].y, y); y = fmaf(e2, w[k].z, y); y = fmaf(e3, w[k].w, y);
-    }
-    z = warp_sum(z); y = warp_sum(y);
-    if (lane == 0) { red[1][warp] = z; red[2][warp] = y; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float zz = 0.f, yy = 0.f;
-#pragma unroll
-      for (int q = 0; q < ROW_THREADS / 32; ++q) { zz += red[1][q]; yy += red[2][q]; }
-      const float Mn = fmaxf(M, m);
-      const float fa = fast_exp(M - Mn), fb = fast_exp(m - Mn);             // exp(-inf) = 0 on the first chunk
-      Z = Z * fa + zz * fb;
-      Yv = Yv * fa + yy * fb;
-      M = Mn;
-    }
-    __syncthreads();                                          // red[] is reused by the next chunk
-  }
-  if (threadIdx.x == 0) {
-    const float inv = 1.0f / Z;
-    rowstat[((size_t)c * n_bags + b) * T + t] = make_float2(M, inv);
     Y[((size_t)b * T + t) * C + c] = Yv * inv;
   }
 }
@@ -446,12 +401,18 @@ welford_cols_kernel(const float* __restrict__ logits, const float2* __restrict__
 }
 
 int welford_split(int n_cblk, int C, int T) {
-  // Sample groups per (column block, head).  The kernel runs 4 CTAs per SM (592 CTA slots on a B200): with at least
-  // one full wave of blocks there is nothing to gain (config 2: splitting the 100 samples in two made the kernel 30 %
-  // slower — partial writes, atomics, a second tail); with fewer blocks (one bag, or one large bag) the samples are
-  // split so that the grid fills the slots once, at least 16 samples per group.
-  const long long ctas = (long long)n_cblk * C, slots = 4 * 148;
-  if (ctas >= slots) return 1;
+  // Sample groups per (column block, head).  The kernel runs up to 4 CTAs per SM (592 CTA slots on a B200): with at
+  // least one full wave of blocks there is nothing to gain (config 2: splitting the 100 samples in two made the kernel
+  // 30 % slower — partial writes, atomics, a second tail); with fewer blocks (one bag, or one large bag) the samples
+  // are split so that the grid gives every SM about three CTAs, at least 16 samples per group.  (Config 4, 128
+  // blocks: 2 / 3 / 4 / 8 / 9 / 16 groups measured 35.4 / 34.2 / 37.5-40.0 / 39.2 / 38.7 / 42.7 us — a CTA's prologue,
+  // partial write and arrival atomic are not free, and a plain read of the same 131 MB needs ~27-30 us:
+  // profiles/r2_experiments.md.)
+  const long long ctas = (long long)n_cblk * C, slots = 3 * 148;
+  if (ctas >= 4 * 148) return 1;
+#ifdef MCMIL_EXP_WSPLIT       // timing experiments: a fixed split below one wave
+  return (MCMIL_EXP_WSPLIT) <= T / 16 ? (MCMIL_EXP_WSPLIT) : (T / 16 < 1 ? 1 : T / 16);
+#endif
   long long s = slots / ctas;
   if (s > COL_MAX_SPLIT) s = COL_MAX_SPLIT;
   if (s > T / 16) s = T / 16;
@@ -473,17 +434,17 @@ cudaError_t launch_reduce(const Plan& p, const float* logits, const float* score
     const unsigned warp_grid = (unsigned)((rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32));
     cudaError_t e;
     // one warp per row when there are enough rows to fill the GPU that way and the rows are not so long that a
-    // CTA per row streams them better
-    if (p.max_n <= 128 * ROWW_V4 && rows >= 2048) {
-      PdlLaunch L(dim3(warp_grid), dim3(ROW_THREADS), 0, st);
-      e = cudaLaunchKernelEx(&L.cfg, softmax_rows_warp_kernel<false>, logits, scores, cu, pcol, n_bags, T, C, Rp, rowstat, Y, wcount, n_wcount);
-    } else if (p.max_n <= 8192 && rows >= 2048) {
-      PdlLaunch L(dim3(warp_grid), dim3(ROW_THREADS), 0, st);
-      e = cudaLaunchKernelEx(&L.cfg, softmax_rows_warp_kernel<true>, logits, scores, cu, pcol, n_bags, T, C, Rp, rowstat, Y, wcount, n_wcount);
-    } else {
-      PdlLaunch L(dim3((unsigned)rows), dim3(ROW_THREADS), 0, st);
-      e = cudaLaunchKernelEx(&L.cfg, softmax_rows_cta_kernel, logits, scores, cu, pcol, n_bags, T, C, Rp, rowstat, Y, wcount, n_wcount);
-    }
+    // CTA per row streams them better; otherwise a CTA per row with the smallest chunk that covers the longest bag
+    auto launch = [&](auto kernel, unsigned grid) {
+      PdlLaunch L(dim3(grid), dim3(ROW_THREADS), 0, st);
+      return cudaLaunchKernelEx(&L.cfg, kernel, logits, scores, cu, pcol, n_bags, T, C, Rp, rowstat, Y, wcount, n_wcount);
+    };
+    if (p.max_n <= 128 * ROWW_V4 && rows >= 2048) e = launch(softmax_rows_warp_kernel<false, 1, ROWW_V4>, warp_grid);
+    else if (p.max_n <= 8192 && rows >= 2048) e = launch(softmax_rows_warp_kernel<true, 1, ROWW_V4>, warp_grid);
+    else if (p.max_n <= ROW_WARPS * 128 * 1) e = launch(softmax_rows_warp_kernel<true, ROW_WARPS, 1>, (unsigned)rows);
+    else if (p.max_n <= ROW_WARPS * 128 * 2) e = launch(softmax_rows_warp_kernel<true, ROW_WARPS, 2>, (unsigned)rows);
+    else if (p.max_n <= ROW_WARPS * 128 * 4) e = launch(softmax_rows_warp_kernel<true, ROW_WARPS, 4>, (unsigned)rows);
+    else e = launch(softmax_rows_warp_kernel<true, ROW_WARPS, ROWW_V4>, (unsigned)rows);
     if (e != cudaSuccess) return e;
   }
   if (launches) ++*launches;

@@ -140,18 +140,19 @@ def test_golden_inkernel_philox(mm, name, impl):
 
 
 def test_reduction_dispatch_variants_agree(mm):
-    """The row kernel has three forms (warp per row in one chunk / in 1024-patch chunks merged on the fly / CTA per
-    row) and the column kernel splits the MC samples over 1..16 CTAs per tile; which one runs depends on the batch
-    shape.  The same bags packed into batches that select different forms give the same outputs up to fp32
-    summation-order rounding, and every form is run-to-run deterministic."""
+    """The row kernel has several forms (warp per row in one chunk / in 1024-patch chunks merged on the fly / CTA per
+    row with 128-, 256-, 512- or 1024-patch chunks per warp) and the column kernel splits the MC samples over 1..16
+    CTAs per tile; which one runs depends on the batch shape.  The same bags packed into batches that select
+    different forms give the same outputs up to fp32 summation-order rounding, and every form is run-to-run
+    deterministic."""
     dev = torch.device("cuda")
     sd = G.make_weights(72, 2, True)
     w = mm.HeadWeights({k: torch.from_numpy(v) for k, v in sd.items()}, dev)
     T = 40
-    lens = [700, 1500, 90]
+    lens = [700, 1500, 90, 3000, 5000]       # alone: one chunk per warp of 128 / 256 / 128 / 512 patches, 1024-patch chunks
     g = torch.Generator(device=dev).manual_seed(5)
     Hs = [torch.relu(torch.randn(n, 512, generator=g, device=dev)) for n in lens]
-    # (a) each bag alone: few rows -> CTA-per-row kernel, samples split over several CTAs per tile
+    # (a) each bag alone: few rows -> CTA-per-row kernels, samples split over several CTAs per tile
     alone = [mm.mc_head(w, h, T, seed=3, bag_ids=[i], return_attention=True) for i, h in enumerate(Hs)]
     # (b) packed together with enough filler bags that the warp-per-row kernel (chunked: max_n > 1024) runs
     fill = [torch.relu(torch.randn(64, 512, generator=g, device=dev)) for _ in range(30)]
