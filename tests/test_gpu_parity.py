@@ -620,3 +620,16 @@ def test_config5_pipeline_small(mm):
     mean_ref, std_ref = PO.attention_map_stats(ref["A"], pt.tiles, idx, (1, h, w))
     assert np.abs(st.mean_map().cpu().numpy() - mean_ref[:, 0]).max() < 1e-3
     assert np.abs(st.std_map().cpu().numpy() - std_ref[:, 0]).max() < 1e-3
+
+
+@pytest.mark.gpu
+def test_c_client_runs_the_hot_path_without_python(mm, tmp_path):
+    """examples/c_client.c: plain C against the C ABI (weights, plan, forward, Welford outputs); it checks finiteness,
+    normalisation, run-to-run bit identity and tcgen05 vs the fp32 CUDA-core path itself and prints "c client ok"."""
+    import subprocess
+    from tests.test_host_logic import _build_c_client
+    exe = str(tmp_path / "c_client")
+    r = _build_c_client(exe)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0 and "c client ok" in run.stdout, run.stdout + run.stderr

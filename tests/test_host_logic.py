@@ -213,3 +213,25 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert rec["impl"] == "reference" and rec["unit"] == "bags/s" and rec["higher_is_better"] is True
     assert rec["cpu_baseline"]["kind"] in ("reference", "port") and rec["cpu_baseline"]["cores"] >= 1
     assert rec["e2e"]["value"] == rec["value"] and rec["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def _build_c_client(out):
+    """gcc line of examples/c_client.c (plain C99 against include/mcmil_b200.h, the CUDA runtime and the shipped .so)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "montecarlo-gated-mil_b200", "lib")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-O2", "-I" + os.path.join(root, "include"),
+           "-I/usr/local/cuda/include", os.path.join(root, "examples", "c_client.c"), "-L" + lib, "-lmcmil_b200",
+           "-L/usr/local/cuda/lib64", "-lcudart", "-lm", "-Wl,-rpath," + lib, "-Wl,-rpath,/usr/local/cuda/lib64", "-o", out]
+    return subprocess.run(cmd, capture_output=True, text=True)
+
+
+def test_header_is_plain_c_and_a_c_client_links(tmp_path):
+    """include/mcmil_b200.h is the drop-in boundary: it must compile as C99 (no C++-isms, no torch types) and a C
+    program that uses it must link against the shipped library without any other dependency than the CUDA runtime."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "montecarlo-gated-mil_b200", "lib", "libmcmil_b200.so")):
+        import __graft_entry__ as g
+        g.build()
+    r = _build_c_client(str(tmp_path / "c_client"))
+    assert r.returncode == 0, r.stderr
