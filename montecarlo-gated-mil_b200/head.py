@@ -26,8 +26,13 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _raw_stream(device) -> int:
+    """Handle of torch's current stream on `device` (the raw query: no Stream object is built)."""
+    return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
+
+
 def _stream_ptr(device) -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return C.c_void_p(_raw_stream(device))
 
 
 class HeadWeights:
@@ -120,8 +125,19 @@ _plan_cache: dict = {}
 _workspaces: dict = {}
 
 
+_one_bag_cu: dict = {}
+
+
 def _check_cu(what: str, cu_seqlens, R: int) -> np.ndarray:
     """Bag boundaries of a packed batch: host ints, start at 0, end at R, strictly increasing."""
+    if cu_seqlens is None and R > 0:                     # one bag: nothing to check (single-bag call loops)
+        cu = _one_bag_cu.get(R)
+        if cu is None:
+            if len(_one_bag_cu) > 4096:
+                _one_bag_cu.clear()
+            cu = _one_bag_cu[R] = np.array([0, R], np.int32)
+            cu.setflags(write=False)
+        return cu
     cu = np.array([0, R], np.int64) if cu_seqlens is None else np.asarray(cu_seqlens, dtype=np.int64)
     if cu.ndim != 1 or len(cu) < 2 or cu[0] != 0 or cu[-1] != R or np.any(np.diff(cu) <= 0):
         raise ValueError(f"{what}: cu_seqlens must start at 0, end at the number of packed rows ({R}) and be "
@@ -140,14 +156,15 @@ def _get_plan(cu: np.ndarray, T: int, C_: int, device, bag_ids=None) -> _Plan:
     return p
 
 
-def _get_workspace(nbytes: int, device) -> torch.Tensor:
-    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < nbytes:
+def _get_workspace(nbytes: int, device, stream: Optional[int] = None) -> int:
+    """Address of a 1024-byte aligned scratch area of `nbytes` private to (device, stream); grown on demand and kept."""
+    key = (device.index, _raw_stream(device) if stream is None else stream)
+    ent = _workspaces.get(key)
+    if ent is None or ent[1] < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20) + 1024, dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
-    off = (-ws.data_ptr()) % 1024
-    return ws[off:off + nbytes]
+        base = ws.data_ptr()
+        ent = _workspaces[key] = (ws, ws.numel() - 1024, base + (-base) % 1024)
+    return ent[2]
 
 
 @dataclass
@@ -242,19 +259,22 @@ def mc_head(weights: HeadWeights, H: torch.Tensor, T: int, seed: int = 0,
         prev = torch.cuda.current_device()
         torch.cuda.set_device(dev)
     try:
+        # three allocations (per-sample logits | both probability statistics | both attention statistics), views for
+        # the rest: every torch.empty costs ~2.5 us of host time, which counts on single-bag call loops
         Y = torch.empty((n_bags, T, C_), dtype=torch.float32, device=dev)
         A = torch.empty((T, C_, R), dtype=torch.float32, device=dev) if return_attention else None
-        pm = torch.empty((n_bags, C_), dtype=torch.float32, device=dev)
-        pq = torch.empty((n_bags, C_), dtype=torch.float32, device=dev)
-        am = torch.empty((C_, R), dtype=torch.float32, device=dev)
-        aq = torch.empty((C_, R), dtype=torch.float32, device=dev)
-        ws = _get_workspace(plan.ws_bytes, dev)
+        pmq = torch.empty((2, n_bags, C_), dtype=torch.float32, device=dev)
+        amq = torch.empty((2, C_, R), dtype=torch.float32, device=dev)
+        pm, pq, am, aq = pmq[0], pmq[1], amq[0], amq[1]
+        stream = _raw_stream(dev)
+        ws_ptr = _get_workspace(plan.ws_bytes, dev, stream)
         fwd = lib.mcmil_head_forward if H.dtype == torch.float32 else lib.mcmil_head_forward_f16
-        code = fwd(weights._h, plan._h, _ptr(H), int(t_offset), int(bag_offset),
+        p_pm, p_am = pmq.data_ptr(), amq.data_ptr()
+        code = fwd(weights._h, plan._h, H.data_ptr(), int(t_offset), int(bag_offset),
                    int(seed) & 0xFFFFFFFFFFFFFFFF, int(philox_rounds), float(p_f), float(p_a),
                    _ptr(keep_f_bits), _ptr(keep_a_bits), _lib.IMPLS[impl],
-                   _ptr(Y), _ptr(A), _ptr(pm), _ptr(pq), _ptr(am), _ptr(aq),
-                   _ptr(ws), ws.numel(), _stream_ptr(dev))
+                   Y.data_ptr(), _ptr(A), p_pm, p_pm + 4 * n_bags * C_, p_am, p_am + 4 * C_ * R,
+                   ws_ptr, plan.ws_bytes, stream)
         _lib.check(code, "mcmil_head_forward")
         launches = int(lib.mcmil_last_launch_count())
     finally:
@@ -341,7 +361,7 @@ class MCHeadRunner:
             raise ValueError(f"MCHeadRunner.run: H must be a contiguous float32 ({self.R}, {L_FEAT}) tensor on {self.dev}")
         slot = self.slots[self._next]
         if self.n_streams == 1:
-            stream = torch.cuda.current_stream(self.dev).cuda_stream
+            stream = _raw_stream(self.dev)
         else:
             self._next = (self._next + 1) % self.n_streams
             if sync_input:
@@ -434,9 +454,9 @@ def debug_proj_tc(weights: HeadWeights, H: torch.Tensor, T: int, seed: int, p_f:
         dbg = torch.zeros((sms, 128, 136), dtype=torch.float32, device=dev)
         lg = torch.zeros((T, weights.num_classes, Rp), dtype=torch.float32, device=dev)
         sc = torch.zeros_like(lg)
-        ws = _get_workspace(plan.ws_bytes, dev)
         _lib.check(lib.mcmil_debug_proj_tc(weights._h, plan._h, _ptr(H), int(t_offset), int(bag_offset),
                                            int(seed), float(p_f), float(p_a), _ptr(keep_f_bits), _ptr(keep_a_bits),
-                                           _ptr(dbg), _ptr(lg), _ptr(sc), _ptr(ws), ws.numel(), _stream_ptr(dev)),
+                                           _ptr(dbg), _ptr(lg), _ptr(sc), _get_workspace(plan.ws_bytes, dev),
+                                           plan.ws_bytes, _stream_ptr(dev)),
                    "mcmil_debug_proj_tc")
     return dbg, lg, sc
