@@ -62,12 +62,16 @@ struct MaskSpec {
 struct PdlLaunch {
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
-  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  // pdl = false: a plain stream-ordered launch.  Used for SM-limited plans (several single-bag calls side by side on
+  // private streams): a projection kernel launched early camps on its SMs in griddepcontrol.wait while the reduction
+  // kernels of its own stream look for room on a GPU whose other SMs are held by the other streams' projections —
+  // measured 45-50 us per bag with the attribute against 25-31 us without (profiles/r2_experiments.md §4).
+  PdlLaunch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl = true) {
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     static const bool off = getenv("MCMIL_NO_PDL") != nullptr;     // A/B switch
-    cfg.attrs = attr; cfg.numAttrs = off ? 0 : 1;
+    cfg.attrs = attr; cfg.numAttrs = (off || !pdl) ? 0 : 1;
   }
 };
 

@@ -828,7 +828,7 @@ cudaError_t launch_proj_tc(const Weights& w, const Plan& p, const MaskSpec& m, c
     const int mask_mode = m.inj_feat != nullptr ? MASK_INJECTED : MASK_PHILOX;
     const KernelFn fn = dbg != nullptr ? debug_kernel : kernels[m.rounds == 7 ? 1 : 0][mask_mode][P.n_out - 1];
     {
-      PdlLaunch L(dim3(2 * n_pairs), dim3(TC_THREADS), SM_TOTAL, st);
+      PdlLaunch L(dim3(2 * n_pairs), dim3(TC_THREADS), SM_TOTAL, st, p.sm_limit == 0);
       cudaError_t e = cudaLaunchKernelEx(&L.cfg, fn, P);
       if (e != cudaSuccess) return e;
     }

@@ -436,7 +436,7 @@ cudaError_t launch_reduce(const Plan& p, const float* logits, const float* score
     // one warp per row when there are enough rows to fill the GPU that way and the rows are not so long that a
     // CTA per row streams them better; otherwise a CTA per row with the smallest chunk that covers the longest bag
     auto launch = [&](auto kernel, unsigned grid) {
-      PdlLaunch L(dim3(grid), dim3(ROW_THREADS), 0, st);
+      PdlLaunch L(dim3(grid), dim3(ROW_THREADS), 0, st, p.sm_limit == 0);
       return cudaLaunchKernelEx(&L.cfg, kernel, logits, scores, cu, pcol, n_bags, T, C, Rp, rowstat, Y, wcount, n_wcount);
     };
     if (p.max_n <= 128 * ROWW_V4 && rows >= 2048) e = launch(softmax_rows_warp_kernel<false, 1, ROWW_V4>, warp_grid);
@@ -450,7 +450,7 @@ cudaError_t launch_reduce(const Plan& p, const float* logits, const float* score
   if (launches) ++*launches;
   const int bag_blocks = (p.n_bags + COL_WARPS - 1) / COL_WARPS;
   {
-    PdlLaunch L(dim3(p.n_cblk + bag_blocks, p.C, p.wsplit), dim3(COL_THREADS), 0, st);
+    PdlLaunch L(dim3(p.n_cblk + bag_blocks, p.C, p.wsplit), dim3(COL_THREADS), 0, st, p.sm_limit == 0);
     const float2* rs = rowstat;
     const int4* cblk = p.d_cblk;
     const float* Yc = Y;

@@ -16,14 +16,16 @@ w = mm.HeadWeights(bench.make_state_dict(0, True), dev)
 H = torch.relu(torch.randn(16 * 1024, 512, device=dev))
 calls = 400
 import itertools
-for k, reserve in [(1, 0)] + list(itertools.product((4, 6, 8), (0, 8, 16, 28))):
+ks = tuple(int(x) for x in sys.argv[1].split(",")) if len(sys.argv) > 1 else (4, 6, 8)
+reserves = tuple(int(x) for x in sys.argv[2].split(",")) if len(sys.argv) > 2 else (0, 8, 16, 28)
+for k, reserve in [(1, 0)] + list(itertools.product(ks, reserves)):
     r = mm.MCHeadRunner(w, 1024, 100, n_streams=k, reserve_sms=reserve)
     for i in range(40):
         r.run(H[(i % 16) * 1024:(i % 16 + 1) * 1024], seed=i)
     r.synchronize(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(calls):
-        r.run(H[(i % 16) * 1024:(i % 16 + 1) * 1024], seed=i)
+        r.run(H[(i % 16) * 1024:(i % 16 + 1) * 1024], seed=i, sync_input=False)
     t_issue = time.perf_counter() - t0
     r.synchronize(); torch.cuda.synchronize()
     dt = time.perf_counter() - t0
