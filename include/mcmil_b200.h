@@ -82,7 +82,8 @@ int mcmil_plan_plane_cols(const mcmil_plan_t* p);
 /* Limits the projection kernel of calls with this plan to `sms` streaming multiprocessors (0 = all; rounded down to
  * CTA pairs, at least one).  Several single-bag calls issued on DIFFERENT streams then run side by side, each on its
  * share of the GPU, and the fixed per-kernel cost of one call (prologue, pipeline fill, tail: ~10 of ~33 us for one
- * bag of 1024 patches, T = 100) overlaps with the steady state of the others.  Results do not depend on the limit. */
+ * bag of 1024 patches, T = 100) overlaps with the steady state of the others.  Results do not depend on the limit.
+ * Calls with a limited plan are launched without programmatic dependent launch (see internal.h, PdlLaunch). */
 int mcmil_plan_set_sm_limit(mcmil_plan_t* p, int sms);
 int mcmil_plan_bag_plane_col(const mcmil_plan_t* p, int bag);
 

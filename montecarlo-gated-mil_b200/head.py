@@ -319,7 +319,10 @@ class MCHeadRunner:
     n_streams = k > 1 (throughput mode): consecutive calls go round-robin to k private streams, each with its own
     buffers, and the projection kernel of a call is limited to 1/k of the SMs (`mcmil_plan_set_sm_limit`), so k bags
     are in flight side by side and the fixed per-kernel cost of a single-bag call (~10 of ~33 us) overlaps with the
-    other bags' steady state.  Per-bag latency grows ~k times, bags/s approach the packed-batch rate.  The result
+    other bags' steady state.  Per-bag latency grows ~k times, bags/s reach the packed-batch rate (N=1024, T=100,
+    k=8: 27 us per bag from a Python loop, 25 us from CUDA graphs, against 44 us on one stream).  SM-limited plans
+    are launched without programmatic dependent launch (an early-launched projection kernel would hold the SMs its
+    own stream's reduction kernels need).  The result
     of a call is valid until k further calls; wait for it with `result.stream.synchronize()` (or `synchronize()`
     for all), the input H must stay untouched until then."""
 
