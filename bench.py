@@ -601,6 +601,9 @@ def run_ours(args):
             tp[f"streams_{k}"].update({"graph_replay_us_per_bag": dtg * 1e6, "graph_replay_bags_per_s": 1.0 / dtg})
             del graphs, rk
         single["throughput_mode"] = tp
+        # the back-to-back rate of single-bag calls a serving loop reaches with 8 calls in flight (Python host loop)
+        single["bags_per_s_8_streams"] = tp["streams_8"]["bags_per_s"]
+        single["us_per_bag_8_streams"] = tp["streams_8"]["us_per_bag"]
 
     # ---- configs 3 and 4 of BASELINE.json, strong scaling over the ranks of this run
     def config3_leg():
