@@ -34,24 +34,12 @@ __device__ __forceinline__ float fast_exp(float x) {
 __device__ __forceinline__ float fast_rcp(float x) {
   float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
 __device__ __forceinline__ void grid_dep_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");               // results of the previous kernel in the stream
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
-// Welford update / Chan merge, shared by both paths
-__device__ __forceinline__ void wf_push(float& mean, float& m2, float a, float inv_cnt) {
-  const float d = a - mean;
-  mean = fmaf(d, inv_cnt, mean);
-  m2 = fmaf(d, a - mean, m2);
-}
+// Chan merge of two (count, mean, M2) partials
 __device__ __forceinline__ void wf_merge(float& n_a, float& mu, float& q, float n_b, float mb, float qb) {
   if (n_b <= 0.f) return;
   const float n_ab = n_a + n_b, dlt = mb - mu;
